@@ -1,0 +1,69 @@
+// Host build of the pixel-stage arithmetic in pyjpegdecoder_b200/csrc/bj_pixel_math.cuh.
+// TEST-ONLY: lets the CPU test-suite check the exact fp32 operation sequence the CUDA kernel runs
+// (the header is __host__ __device__ and uses explicit fmaf only).  Never used by the product.
+#include <cstdint>
+#include <cmath>
+#include "../../pyjpegdecoder_b200/csrc/bj_pixel_math.cuh"
+
+extern "C" {
+
+// blocks: n x 64 dequantised coefficients in natural order [v*8+u] (as int32).
+// out: n x 64 rounded samples (+128) [y*8+x]; flagged: n bytes, 1 if the kernel would recompute the block exactly.
+void hs_idct_blocks(const int32_t* blocks, int n, int16_t* out, uint8_t* flagged, float* min_tie_dist) {
+    for (int b = 0; b < n; b++) {
+        float f[64];
+        float S = 0.f;
+        for (int k = 0; k < 64; k++) {
+            f[k] = (float)blocks[b * 64 + k];
+            S += fabsf(f[k]);
+        }
+        bj::idct8x8_fast(f);
+        const float T = fmaf(S, BJ_IDCT_ERR_REL, BJ_IDCT_ERR_ABS);
+        float mind = 1.0f;
+        for (int k = 0; k < 64; k++) {
+            float td;
+            float r = bj::round_tie(f[k], td);
+            mind = fminf(mind, td);
+            out[b * 64 + k] = (int16_t)((int)r + 128);
+        }
+        flagged[b] = mind < T;
+        if (min_tie_dist) min_tie_dist[b] = mind;
+    }
+}
+
+// weights of kind (rh, rv) for MCU pixel (b, a): w[b*16+a][4] = w00,w10,w01,w11 and cell i,j
+void hs_weights(int rh, int rv, int32_t* w, int32_t* cell) {
+    for (int b = 0; b < 16; b++)
+        for (int a = 0; a < 16; a++) {
+            int ii = a & 7, s = 0, jj = b & 7, t = 0;
+            if (rh == 2) bj::up_cell(a, ii, s);
+            if (rv == 2) bj::up_cell(b, jj, t);
+            int w00, w10, w01, w11;
+            bj::up_weights_2d(ii, jj, s, t, w00, w10, w01, w11);
+            int32_t* o = w + (b * 16 + a) * 4;
+            o[0] = w00; o[1] = w10; o[2] = w01; o[3] = w11;
+            cell[(b * 16 + a) * 2] = ii;
+            cell[(b * 16 + a) * 2 + 1] = jj;
+        }
+}
+
+float hs_div15(float n) { return bj::div15_round(n); }
+
+// colour fast path for n pixels; tie[i] = 1 when the kernel would take the fp64 path
+void hs_color(const int16_t* ycc, int n, uint8_t* rgb, uint8_t* tie) {
+    for (int i = 0; i < n; i++) {
+        float R, G, B, err;
+        bj::ycc_to_rgb_fast((float)ycc[3 * i], (float)ycc[3 * i + 1], (float)ycc[3 * i + 2], R, G, B, err);
+        float v[3] = {R, G, B};
+        bool t = false;
+        for (int c = 0; c < 3; c++) {
+            float w = v[c] + BJ_MAGIC;
+            float r = w - BJ_MAGIC;
+            t = t || ((0.5f - fabsf(v[c] - r)) < err && v[c] > -1.0f && v[c] < 256.0f);
+            int iv = (int)r;
+            rgb[3 * i + c] = (uint8_t)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
+        }
+        tie[i] = t;
+    }
+}
+}

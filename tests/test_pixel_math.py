@@ -1,0 +1,147 @@
+"""CPU checks of the pixel-stage arithmetic (host build of csrc/bj_pixel_math.cuh) against the oracle.
+
+The CUDA kernel accepts an fp32 result only when it is farther from a rounding tie than the error
+bound; these tests check that this rule never accepts a wrong value, and that the interpolation
+weights equal the reference's griddata weights.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+from hostsim import build
+
+ZZ_NAT = None
+
+
+@pytest.fixture(scope="module")
+def hs():
+    L = build("pixel_hostsim")
+    L.hs_div15.restype = ctypes.c_float
+    L.hs_div15.argtypes = [ctypes.c_float]
+    return L
+
+
+def _idct(hs, blocks_nat):
+    n = blocks_nat.shape[0]
+    b = np.ascontiguousarray(blocks_nat, dtype=np.int32)
+    out = np.empty((n, 64), np.int16)
+    flg = np.empty(n, np.uint8)
+    dist = np.empty(n, np.float32)
+    hs.hs_idct_blocks(b.ctypes.data_as(ctypes.c_void_p), n, out.ctypes.data_as(ctypes.c_void_p),
+                      flg.ctypes.data_as(ctypes.c_void_p), dist.ctypes.data_as(ctypes.c_void_p))
+    return out, flg.astype(bool), dist
+
+
+def _oracle_idct(blocks_nat):
+    # oracle wants block[u, v]; natural order is [v, u]; oracle returns [x, y]; we want [y, x]
+    out = np.empty((blocks_nat.shape[0], 64), np.int16)
+    for i, b in enumerate(blocks_nat):
+        o = oracle.idct_block(b.reshape(8, 8).T.astype(np.int16))
+        out[i] = o.T.reshape(64)
+    return out
+
+
+def _random_blocks(rng, n, mode):
+    b = np.zeros((n, 64), np.int32)
+    if mode == "dense":
+        b[:] = rng.integers(-600, 600, (n, 64))
+    elif mode == "sparse":
+        mask = rng.random((n, 64)) < 0.15
+        b[mask] = rng.integers(-300, 300, mask.sum())
+        b[:, 0] = rng.integers(-1024, 1024, n)
+    elif mode == "dc_only":
+        b[:, 0] = rng.integers(-1024, 1024, n) * rng.integers(1, 20, n)
+    elif mode == "ties":
+        # DC = 8k+4 -> every sample is exactly k + 0.5: the reference decides by fp64 noise
+        b[:, 0] = 8 * rng.integers(-120, 120, n) + 4
+        m = rng.random(n) < 0.5
+        b[m, 32] = 8 * rng.integers(-5, 5, m.sum())   # (v=4,u=0): keeps many samples on ties
+    elif mode == "large":
+        b[:] = rng.integers(-32768, 32767, (n, 64))
+    return b
+
+
+@pytest.mark.parametrize("mode", ["dense", "sparse", "dc_only", "ties", "large"])
+def test_idct_fast_path_never_accepts_a_wrong_sample(hs, mode):
+    rng = np.random.default_rng(hash(mode) & 0xFFFF)
+    b = _random_blocks(rng, 1500, mode)
+    fast, flagged, _ = _idct(hs, b)
+    want = _oracle_idct(b)
+    ok = ~flagged
+    assert np.array_equal(fast[ok], want[ok])
+    if mode == "ties":
+        assert flagged.all()          # every such block must go to the exact path
+    if mode == "sparse":
+        assert flagged.mean() < 0.2   # and the exact path stays rare on ordinary content
+
+
+def test_idct_fast_path_on_real_coefficients(hs):
+    """Dequantised blocks of real files: fast path result == oracle wherever it is accepted."""
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    from pyjpegdecoder_b200.layout import ZIGZAG_UV
+    nat_of_zz = np.array([v * 8 + u for (u, v) in ZIGZAG_UV])
+    for name in ["base_120x88_ss2_q95", "base_256x128_ss2_opt", "base_sat_96x64_ss0", "prog_200x120_ss0"]:
+        data = (GOLDEN / "cases" / f"{name}.jpg").read_bytes()
+        p = parse_jpeg(data)
+        r = oracle.decode(data)
+        for ci, c in enumerate(p.components):
+            q = p.qtables[c.tq].astype(np.int32)
+            zz = r.coef[ci].reshape(-1, 64).astype(np.int32)
+            deq = (zz * q).astype(np.int16).astype(np.int32)
+            nat = np.zeros_like(deq)
+            nat[:, nat_of_zz] = deq
+            fast, flagged, _ = _idct(hs, nat)
+            want = _oracle_idct(nat)
+            assert np.array_equal(fast[~flagged], want[~flagged]), name
+
+
+@pytest.mark.parametrize("kind,key", [((2, 2), "w_8x8_16x16"), ((2, 1), "w_8x8_16x8"), ((1, 2), "w_8x8_8x16")])
+def test_interpolation_weights_match_griddata(hs, kind, key):
+    rh, rv = kind
+    w = np.zeros((256, 4), np.int32)
+    cell = np.zeros((256, 2), np.int32)
+    hs.hs_weights(rh, rv, w.ctypes.data_as(ctypes.c_void_p), cell.ctypes.data_as(ctypes.c_void_p))
+    gold = np.load(GOLDEN / "upsample_weights.npz")[key]   # [i, j, a, b] weights * 15
+    for b in range(8 * rv):
+        for a in range(8 * rh):
+            i, j = cell[b * 16 + a]
+            dense = np.zeros((8, 8), np.int64)
+            for (di, dj, k) in ((0, 0, 0), (1, 0, 1), (0, 1, 2), (1, 1, 3)):
+                if w[b * 16 + a, k]:
+                    dense[min(i + di, 7), min(j + dj, 7)] += w[b * 16 + a, k]
+            assert np.array_equal(dense, gold[:, :, a, b]), (a, b)
+            assert w[b * 16 + a].sum() == 15
+
+
+def test_div15_round_exact(hs):
+    n = np.arange(-15 * 4000, 15 * 4000 + 1)
+    want = np.floor_divide(2 * n + 15, 30)
+    got = np.array([hs.hs_div15(float(x)) for x in n[::7]])
+    assert np.array_equal(got, want[::7])
+
+
+def test_colour_fast_path_never_accepts_a_wrong_pixel(hs):
+    rng = np.random.default_rng(5)
+    n = 400000
+    ycc = np.empty((n, 3), np.int16)
+    ycc[:, 0] = rng.integers(-40, 300, n)
+    ycc[:, 1] = rng.integers(-60, 320, n)
+    ycc[:, 2] = rng.integers(-60, 320, n)
+    # exact decimal ties of the colour matrix: Cr-128 = +-250, Cb-128 = +-125
+    ycc[:2000, 2] = 128 + 250
+    ycc[2000:4000, 1] = 128 + 125
+    ycc[4000:6000, 1] = 3
+    rgb = np.empty((n, 3), np.uint8)
+    tie = np.empty(n, np.uint8)
+    hs.hs_color(ycc.ctypes.data_as(ctypes.c_void_p), n, rgb.ctypes.data_as(ctypes.c_void_p), tie.ctypes.data_as(ctypes.c_void_p))
+    Y, Cb, Cr = (ycc[:, k].astype(np.float64) for k in range(3))
+    R = Y + 1.402 * (Cr - 128.0)
+    G = Y - 0.34414 * (Cb - 128.0) - 0.71414 * (Cr - 128.0)
+    B = Y + 1.772 * (Cb - 128.0)
+    want = np.round(np.clip(np.stack((R, G, B), -1), 0.0, 255.0)).astype(np.uint8)   # jpeg_decoder.py:1693-1700
+    ok = tie == 0
+    assert np.array_equal(rgb[ok], want[ok])
+    assert tie.mean() < 0.05
