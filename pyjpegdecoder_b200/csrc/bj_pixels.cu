@@ -163,7 +163,7 @@ __device__ __forceinline__ int clamp_round_u8(float v, float err, bool& tie) {
 
 template <int HX>
 __device__ __forceinline__ void pixel_run(Smem& sm, const bj_image& im, int out_kind, int m, int mblk0, int r,
-                                          int row_stride_s, void* out, int64_t gbase, uint32_t* stats) {
+                                          int row_stride_s, int cols, void* out, int64_t gbase, uint32_t* stats) {
     float y[8];
     comp_run_any<HX>(sm, im, 0, mblk0, r, y);
     const int px0 = m * 8 * im.hmax + 8 * HX;  // pixel x inside the strip
@@ -181,7 +181,8 @@ __device__ __forceinline__ void pixel_run(Smem& sm, const bj_image& im, int out_
         } else {
             int16_t* o = reinterpret_cast<int16_t*>(out) + gbase + (int64_t)r * im.out_pitch + px0;
 #pragma unroll
-            for (int p = 0; p < 8; p++) o[p] = (int16_t)y[p];
+            for (int p = 0; p < 8; p++)
+                if (px0 + p < cols) o[p] = (int16_t)y[p];
         }
         return;
     }
@@ -192,6 +193,7 @@ __device__ __forceinline__ void pixel_run(Smem& sm, const bj_image& im, int out_
         int16_t* o = reinterpret_cast<int16_t*>(out) + gbase + (int64_t)r * im.out_pitch + (int64_t)px0 * 3;
 #pragma unroll
         for (int p = 0; p < 8; p++) {
+            if (px0 + p >= cols) break;
             o[3 * p] = (int16_t)y[p];
             o[3 * p + 1] = (int16_t)cb[p];
             o[3 * p + 2] = (int16_t)cr[p];
@@ -394,8 +396,8 @@ bj_pixels_kernel(const bj_image* __restrict__ images, const void* __restrict__ i
         int r = pair / im.hmax, hx = pair % im.hmax;
         int m = (chunk << 5) + lane;
         if (r >= rows || m >= M) continue;
-        if (hx) pixel_run<1>(sm, im, out_kind, m, m * bpm, r, row_stride_s, out, gbase, stats);
-        else pixel_run<0>(sm, im, out_kind, m, m * bpm, r, row_stride_s, out, gbase, stats);
+        if (hx) pixel_run<1>(sm, im, out_kind, m, m * bpm, r, row_stride_s, cols, out, gbase, stats);
+        else pixel_run<0>(sm, im, out_kind, m, m * bpm, r, row_stride_s, cols, out, gbase, stats);
     }
     if (out_kind != BJ_OUT_RGB) return;
     __syncthreads();
