@@ -80,6 +80,120 @@ typedef struct bj_image {
     uint32_t reserved;
 } bj_image;
 
+/* ---------------------------------------------------------------------------------------------
+ * Entropy stage descriptors.
+ *
+ * A SCAN is one SOS segment of one image (jpeg_decoder.py:505-652).  Its entropy-coded bytes are
+ * split by restart markers into STREAMS (restart intervals, :898-900 / :1050-1053 / :1297-1298);
+ * a scan without DRI is one stream.  Every stream is decoded by many threads: it is cut into
+ * SUBSEQUENCES of BJ_SUBSEQ_BITS bits that are decoded speculatively and then stitched together
+ * (self-synchronising Huffman decode), see DESIGN.md.
+ * ------------------------------------------------------------------------------------------- */
+#define BJ_SUBSEQ_BITS 1024
+#define BJ_ENTROPY_THREADS 128 /* subsequences per CTA */
+#define BJ_UNSTUFF_TILE 4096   /* raw bytes per CTA of the un-stuffing kernels */
+
+#define BJ_MODE_BASELINE 0  /* baseline_dct_scan           :697-906   */
+#define BJ_MODE_DC_FIRST 1  /* progressive DC first        :983-1033  */
+#define BJ_MODE_DC_REFINE 2 /* progressive DC refinement   :1036-1043 */
+#define BJ_MODE_AC_FIRST 3  /* progressive AC first + EOB runs :1120-1256 */
+#define BJ_MODE_AC_REFINE 4 /* progressive AC refinement   :1100-1115, :1183-1198, :1258-1292 */
+
+typedef struct bj_scan {
+    uint64_t raw_off;      /* byte offset of the entropy-coded segment in the raw buffer (any alignment; the buffer
+                              itself is 16-byte aligned and padded with 32 spare bytes) */
+    uint64_t coef_block0;  /* first block of the image in the coefficient buffer */
+    uint32_t raw_len;      /* bytes, including stuffed zeros and restart markers */
+    uint32_t image;        /* index of the per-image error word */
+    uint32_t stream0;      /* first entry of this scan in the stream tables */
+    uint32_t n_streams;    /* ceil(n_mcu / ri), or 1 */
+    uint32_t ri;           /* MCUs per stream (= n_mcu when there is no DRI) */
+    uint32_t n_mcu;        /* MCUs in the scan (:621) */
+    uint32_t mcus_x;       /* scan MCU grid width (:609-619) */
+    uint32_t sub0;         /* first subsequence slot of this scan in the per-subsequence arrays */
+    uint32_t n_sub_max;    /* slots reserved: >= sum over streams of ceil(bits / BJ_SUBSEQ_BITS) */
+    uint32_t lut_off;      /* this scan's Huffman tables in the LUT buffer (uint32 entries) */
+    uint32_t lut_len;
+    uint32_t tile0;        /* first un-stuffing tile of this scan */
+    uint16_t frame_mcus_x; /* interleaved MCU grid width of the frame */
+    uint8_t frame_bpm;     /* blocks per MCU of the frame (coefficient buffer stride) */
+    uint8_t nslots;        /* blocks per MCU of this scan */
+    uint8_t mode;          /* BJ_MODE_* */
+    uint8_t ss, se, ah, al;
+    uint8_t interleaved;   /* 1: block = coef_block0 + mcu*frame_bpm + slot_frame[slot];
+                              0: single component, block grid raster (:612-619), see comp_* */
+    uint8_t comp_h, comp_v, comp_slot0; /* non-interleaved: the component's h, v and first frame slot */
+    uint8_t ncomp_scan;                 /* components in the scan */
+    uint8_t slot_frame[BJ_MAX_SLOTS];   /* scan slot -> slot inside the frame MCU */
+    uint8_t slot_comp[BJ_MAX_SLOTS];    /* scan slot -> component index within the scan (DC predictor) */
+    uint16_t slot_dc[BJ_MAX_SLOTS];     /* scan slot -> DC table offset inside the scan's LUT blob */
+    uint16_t slot_ac[BJ_MAX_SLOTS];     /* scan slot -> AC table offset */
+    uint32_t reserved;
+} bj_scan;
+
+/* Device buffers of the entropy stage (all caller-allocated, see pyjpegdecoder_b200/pipeline.py):
+ *   words        un-stuffed bitstream, big-endian 32-bit words (bit 31 of word 0 = first bit)
+ *   stream_start byte offset of each stream in `words`; stream_end likewise
+ *   stream_sub   first subsequence of each stream, relative to its scan's sub0
+ *   sub_entry/sub_exit  packed decoder state at the start / end of each subsequence
+ *   sub_count    per subsequence: blocks started + DC difference sums of up to 3 components
+ *   sub_prefix   exclusive prefix sums of sub_count (in subsequence order)
+ */
+typedef struct bj_entropy_buffers {
+    const uint32_t* words;
+    uint64_t words_len;     /* in 32-bit words, including 64 words of slack at the end */
+    uint64_t* stream_start;
+    uint64_t* stream_end;
+    uint32_t* stream_sub;
+    uint64_t* sub_entry;
+    uint64_t* sub_exit;
+    uint32_t* sub_count;    /* 4 x uint32 per subsequence */
+    uint32_t* sub_prefix;   /* 4 x uint32 per subsequence */
+    const uint32_t* lut;
+    int16_t* coef;
+    uint32_t* err;          /* per image error word (BJ_ERR_*) */
+    uint32_t* sync_changes; /* optional statistics: subsequences re-decoded by the fix-up pass */
+} bj_entropy_buffers;
+
+/*
+ * Byte un-stuffing + restart-marker removal for every scan of a batch in one pass
+ * (replaces the reader side of bits_generator/get_bits, jpeg_decoder.py:654-695: the byte after
+ * 0xFF is dropped (:676-677); restart markers are skipped (:667-669)).
+ *   raw         all entropy-coded segments, each starting at scan.raw_off
+ *   tile_scan   scan index of every BJ_UNSTUFF_TILE-byte tile; a scan owns
+ *               max(1, ceil(((raw_off & 15) + raw_len) / BJ_UNSTUFF_TILE)) consecutive tiles from tile0
+ *   tile_sum    workspace, uint64[n_tiles + 1]
+ *   words_out   compacted bitstream as big-endian 32-bit words (size >= total raw bytes / 4 + 64)
+ *   stream_start/stream_end  filled per stream; missing restart markers leave UINT64_MAX
+ */
+bj_status bj_unstuff(const uint8_t* raw, const bj_scan* scans, int n_scans, const uint32_t* tile_scan,
+                     int n_tiles, uint64_t* tile_sum, uint32_t* words_out, uint64_t* stream_start,
+                     uint64_t* stream_end, int n_streams_total, void* stream);
+
+/*
+ * Stream planning: after bj_unstuff, computes for every scan the length of each stream, the number of
+ * subsequences per stream and the first subsequence of each stream; flags missing restart markers
+ * (BJ_ERR_RST_COUNT).  tile_sum is the workspace bj_unstuff filled.
+ */
+bj_status bj_entropy_plan(const bj_scan* scans, int scan_first, int n_scans, const uint64_t* tile_sum,
+                          const bj_entropy_buffers* bufs, void* stream);
+
+/*
+ * Entropy decode of scans [scan_first, scan_first + n_scans), all of the same `mode` and independent
+ * of each other (one "wave": normally the k-th scan of every image of the batch).  Replaces
+ * baseline_dct_scan's entropy part (:709-722, :805-866, :898-900) and progressive_dct_scan
+ * (:908-1304); coefficients go straight into the coefficient buffer (zig-zag order, quantised).
+ * Progressive images need their coefficient blocks zeroed before the first scan.
+ *   max_sub      max over the wave's scans of n_sub_max         (baseline / DC first / AC first)
+ *   max_streams  max over the wave's scans of n_streams         (AC refine)
+ *   max_blocks   max over the wave's scans of n_mcu * nslots    (DC refine)
+ *   max_lut      max over the wave's scans of lut_len
+ *   chain        workspace, uint32[8 * ceil(max_sub / BJ_ENTROPY_THREADS) * n_scans]
+ */
+bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, int mode, uint32_t max_sub,
+                            uint32_t max_streams, uint32_t max_blocks, uint32_t max_lut,
+                            const bj_entropy_buffers* bufs, uint32_t* chain, void* stream);
+
 /* Output selector of bj_pixels(). */
 #define BJ_OUT_RGB 0     /* uint8: fused IDCT + upsample + YCbCr->RGB (+ clamp)            */
 #define BJ_OUT_SAMPLES 1 /* int16 sample buffer: de-zigzag, dequantise, IDCT, +128 only    */
@@ -89,7 +203,7 @@ typedef struct bj_image {
 #define BJ_IN_SAMPLES 1  /* sample buffer produced by BJ_OUT_SAMPLES */
 
 int bj_version(void);
-int bj_sizeof(int what); /* 0: sizeof(bj_image) -- lets a binding verify its struct mirror */
+int bj_sizeof(int what); /* 0: sizeof(bj_image), 1: sizeof(bj_scan), 2: sizeof(bj_entropy_buffers) */
 const char* bj_last_cuda_error(void);
 
 /*

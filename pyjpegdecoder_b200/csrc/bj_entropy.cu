@@ -1,0 +1,590 @@
+// bj_entropy.cu -- entropy decoding kernels (sm_100a): stream planning, speculative decode,
+// chained fix-up + prefix sums, and the writing passes for baseline and progressive scans.
+//
+// Replaces the entropy half of baseline_dct_scan (jpeg_decoder.py:709-722, :805-866, :898-900) and
+// progressive_dct_scan (:908-1304).  The per-thread decode logic lives in bj_entropy.cuh (shared with
+// the CPU test-suite); this file is the orchestration:
+//
+//   plan     one CTA per scan: stream lengths -> subsequences per stream -> first subsequence of
+//            every stream (exclusive scan), restart-marker count check.
+//   spec     one thread per subsequence: decode from one subsequence early (assumed block start) to
+//            obtain a speculative entry state, then the own subsequence: exit state, blocks started,
+//            DC difference sums.  The CTA's slice of the bitstream and the scan's Huffman LUTs are
+//            staged in shared memory (bank-swizzled), since every lane walks its own 128-byte region.
+//   fix      ONE launch: each CTA iterates (shared memory) until every subsequence's entry equals its
+//            predecessor's exit, then waits for the previous CTA of the scan to publish its final
+//            exit state and running totals (decoupled look-back chaining: CTAs only wait on
+//            lower-indexed CTAs), repairs if needed, computes the segmented exclusive prefix sums
+//            (block index and DC predictors per subsequence) and publishes its own totals.
+//   write    baseline: each thread owns the blocks that START in its subsequence, assembles each in a
+//            private shared-memory slot and stores it as one 128-byte line -- every block is written
+//            exactly once, no memset, no atomics.  Progressive first scans store single coefficients.
+//   dc refine / ac refine: see the kernels below.
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/b200jpeg.h"
+#include "bj_entropy.cuh"
+
+extern "C" bj_status bj_set_cuda_error(cudaError_t e, const char* where);
+
+namespace {
+
+using namespace bj;
+
+constexpr int T = BJ_ENTROPY_THREADS;
+constexpr int S = BJ_SUBSEQ_BITS;
+constexpr int kWinWords = (T + 1) * (S / 32) + 64;  // bit window of one CTA, in 32-bit words
+constexpr int kMaxLutSmem = 12288;                  // most LUT entries ever staged in shared memory (48 KB)
+
+// chain record per CTA (8 x uint32): exit lo, exit hi, blocks, dc0, dc1, dc2, flag, pad
+constexpr int kChainWords = 8;
+
+struct WinSrc {
+    const uint32_t* sw;  // shared window, swizzled
+    uint32_t w0;         // first word held in the window
+    uint32_t n;          // words in the window
+    const uint32_t* gw;  // global words
+    uint32_t gn;
+    __device__ __forceinline__ uint32_t word(uint32_t i) const {
+        uint32_t j = i - w0;
+        if (j < n) return sw[j ^ ((j >> 5) & 31u)];
+        return i < gn ? __ldg(gw + i) : 0xFFFFFFFFu;
+    }
+};
+
+struct GlobalSrc {
+    const uint32_t* gw;
+    uint32_t gn;
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return i < gn ? __ldg(gw + i) : 0xFFFFFFFFu; }
+};
+
+struct CtaShared {
+    bj_scan sc;
+    ScanCtx ctx;
+    uint32_t scan_nsub;
+    uint32_t win_w0, win_n;
+    uint32_t lut_cap;  // entries available in lut[] (dynamic shared memory)
+    uint32_t win[kWinWords];
+    uint32_t lut[1];   // lut_cap entries follow
+};
+
+// ---- helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_scan(CtaShared& sh, const bj_scan* scans, int idx, const bj_entropy_buffers& B,
+                                          uint32_t lut_cap) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[idx]);
+    for (int i = threadIdx.x; i < (int)(sizeof(bj_scan) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&sh.sc)[i] = src[i];
+    __syncthreads();
+    const bj_scan& sc = sh.sc;
+    const bool in_smem = sc.lut_len <= lut_cap;
+    if (in_smem)
+        for (uint32_t i = threadIdx.x; i < sc.lut_len; i += blockDim.x) sh.lut[i] = __ldg(B.lut + sc.lut_off + i);
+    if (threadIdx.x == 0) {
+        sh.ctx.lut = in_smem ? sh.lut : (B.lut + sc.lut_off);
+        for (int i = 0; i < BJ_MAX_SLOTS; i++) {
+            sh.ctx.dc_tab[i] = sc.slot_dc[i];
+            sh.ctx.ac_tab[i] = sc.slot_ac[i];
+            sh.ctx.slot_comp[i] = sc.slot_comp[i];
+        }
+        sh.ctx.nslots = sc.nslots;
+        sh.ctx.ss = sc.ss;
+        sh.ctx.se = sc.se;
+        sh.ctx.al = sc.al;
+        // total subsequences of the scan = first subsequence of the last stream + its own count
+        uint32_t last = sc.stream0 + sc.n_streams - 1;
+        uint64_t bits = (B.stream_end[last] - B.stream_start[last]) * 8;
+        sh.scan_nsub = B.stream_sub[last] + (uint32_t)((bits + S - 1) / S);
+    }
+    __syncthreads();
+}
+
+struct SubInfo {
+    bool valid;
+    uint32_t stream;     // absolute stream index
+    uint32_t l;          // subsequence index inside the stream
+    uint64_t b0, b1;     // stream bit range
+    uint64_t own, stop;  // own bit range
+    uint32_t nblk_stream;
+    uint32_t mcu0;       // first MCU of the stream
+};
+
+__device__ __forceinline__ SubInfo locate(const CtaShared& sh, const bj_entropy_buffers& B, uint32_t lscan) {
+    SubInfo s;
+    const bj_scan& sc = sh.sc;
+    s.valid = lscan < sh.scan_nsub;
+    if (!s.valid) return s;
+    // last stream m with stream_sub[m] <= lscan
+    uint32_t lo = 0, hi = sc.n_streams - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (B.stream_sub[sc.stream0 + mid] <= lscan) lo = mid;
+        else hi = mid - 1;
+    }
+    s.stream = sc.stream0 + lo;
+    s.l = lscan - B.stream_sub[s.stream];
+    s.b0 = B.stream_start[s.stream] * 8;
+    s.b1 = B.stream_end[s.stream] * 8;
+    s.own = s.b0 + (uint64_t)s.l * S;
+    s.stop = min(s.own + (uint64_t)S, s.b1);
+    s.mcu0 = lo * sc.ri;
+    uint32_t mcus = min(sc.ri, sc.n_mcu - s.mcu0);
+    s.nblk_stream = mcus * sc.nslots;
+    if (s.own >= s.b1) s.valid = false;  // (cannot happen: nsub = ceil(bits / S))
+    return s;
+}
+
+// Stage the CTA's slice of the bitstream: words [w0, w0 + kWinWords).
+__device__ __forceinline__ void load_window(CtaShared& sh, const bj_entropy_buffers& B, uint64_t first_bit) {
+    uint32_t w0 = (uint32_t)(first_bit >> 5);
+    uint32_t gn = (uint32_t)B.words_len;
+    for (uint32_t j = threadIdx.x; j < (uint32_t)kWinWords; j += blockDim.x) {
+        uint32_t i = w0 + j;
+        sh.win[j ^ ((j >> 5) & 31u)] = i < gn ? __ldg(B.words + i) : 0xFFFFFFFFu;
+    }
+    if (threadIdx.x == 0) {
+        sh.win_w0 = w0;
+        sh.win_n = kWinWords;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ WinSrc win_src(const CtaShared& sh, const bj_entropy_buffers& B) {
+    return WinSrc{sh.win, sh.win_w0, sh.win_n, B.words, (uint32_t)B.words_len};
+}
+
+// Decode subsequence `si` from entry state st: exit state + counts.
+template <class Src>
+__device__ __forceinline__ void run_sub(const CtaShared& sh, const Src& src, const SubInfo& si, uint64_t st, uint64_t& ex,
+                                        SubCount& k) {
+    BitReader<Src> rd;
+    rd.seek(&src, state_pos(st));
+    int z = state_z(st), slot = state_slot(st);
+    k.blocks = 0;
+    k.dc[0] = k.dc[1] = k.dc[2] = 0;
+    const int mode = sh.sc.mode;
+    if (mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, sh.ctx, si.own, si.stop, si.b1, k);
+    else if (mode == BJ_MODE_DC_FIRST) sync_run<BJ_M_DCFIRST>(rd, z, slot, sh.ctx, si.own, si.stop, si.b1, k);
+    else {
+        struct NoSink { __device__ void store(uint32_t, int, int16_t) {} } ns;
+        uint32_t blk = 0, adv = 0;
+        acfirst_run<false>(rd, z, sh.ctx, si.own, si.stop, si.b1, blk, 0xFFFFFFFFu, adv, ns);
+        k.blocks = adv;
+    }
+    ex = pack_state(rd.pos, z, slot);
+}
+
+// ---- plan ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plan_kernel(const bj_scan* __restrict__ scans, int scan_first,
+                                                   const uint64_t* __restrict__ tile_sum, bj_entropy_buffers B) {
+    const bj_scan& sc = scans[scan_first + blockIdx.x];
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t carry;
+    __shared__ int bad;
+    if (threadIdx.x == 0) { carry = 0; bad = 0; }
+    __syncthreads();
+    const uint32_t n_tiles = ((uint32_t)(sc.raw_off & 15) + sc.raw_len + BJ_UNSTUFF_TILE - 1) / BJ_UNSTUFF_TILE;
+    const uint64_t scan_end = tile_sum[sc.tile0 + (n_tiles ? n_tiles : 1)] & ((1ull << 40) - 1);
+    for (uint32_t base = 0; base < sc.n_streams; base += 256) {
+        uint32_t m = base + threadIdx.x;
+        uint32_t nsub = 0;
+        uint64_t st = 0, en = 0;
+        if (m < sc.n_streams) {
+            st = B.stream_start[sc.stream0 + m];
+            en = (m + 1 < sc.n_streams) ? B.stream_start[sc.stream0 + m + 1] : scan_end;
+            if (st == ~0ull || en == ~0ull || en < st) {  // restart marker missing
+                bad = 1;
+                st = en = scan_end;
+            }
+            nsub = (uint32_t)(((en - st) * 8 + S - 1) / S);
+        }
+        part[threadIdx.x] = nsub;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            uint32_t a = (threadIdx.x >= (unsigned)o) ? part[threadIdx.x - o] : 0;
+            __syncthreads();
+            part[threadIdx.x] += a;
+            __syncthreads();
+        }
+        if (m < sc.n_streams) {
+            B.stream_start[sc.stream0 + m] = st;
+            B.stream_end[sc.stream0 + m] = en;
+            B.stream_sub[sc.stream0 + m] = carry + part[threadIdx.x] - nsub;
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) carry += part[255];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (bad) atomicOr(&B.err[sc.image], BJ_ERR_RST_COUNT);
+        if (carry > sc.n_sub_max) atomicOr(&B.err[sc.image], BJ_ERR_SYNC);
+    }
+}
+
+// ---- speculative pass ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
+                                                 uint32_t lut_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
+    load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
+    const uint32_t base = blockIdx.x * T;
+    if (base >= sh.scan_nsub) return;
+    const uint32_t lscan = base + threadIdx.x;
+    SubInfo si = locate(sh, B, lscan);
+    // window starts where the first thread starts reading
+    __shared__ uint64_t first_bit;
+    if (threadIdx.x == 0) first_bit = si.l ? si.own - S : si.own;
+    __syncthreads();
+    load_window(sh, B, first_bit);
+    if (!si.valid) return;
+    WinSrc src = win_src(sh, B);
+    const int z0 = (sh.sc.mode == BJ_MODE_AC_FIRST) ? sh.sc.ss : 0;
+    uint64_t st;
+    if (si.l == 0) st = pack_state(si.b0, z0, 0);
+    else {
+        SubInfo warm = si;
+        warm.own = ~0ull;  // nothing is counted while warming up
+        warm.stop = si.own;
+        uint64_t ex;
+        SubCount k;
+        run_sub(sh, src, warm, pack_state(si.own - S, z0, 0), ex, k);
+        st = ex;
+    }
+    uint64_t ex;
+    SubCount k;
+    run_sub(sh, src, si, st, ex, k);
+    const size_t g = (size_t)sh.sc.sub0 + lscan;
+    B.sub_entry[g] = st;
+    B.sub_exit[g] = ex;
+    reinterpret_cast<uint4*>(B.sub_count)[g] = make_uint4(k.blocks, (uint32_t)k.dc[0], (uint32_t)k.dc[1], (uint32_t)k.dc[2]);
+}
+
+// ---- chained fix-up + prefix sums --------------------------------------------------------------------
+__global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
+                                                uint32_t* __restrict__ chain, uint32_t lut_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
+    __shared__ uint64_t s_exit[T];
+    __shared__ uint32_t s_cnt[T][4];
+    __shared__ uint32_t s_head[T];
+    __shared__ uint64_t s_prev_exit;
+    __shared__ uint32_t s_carry[4];
+    __shared__ uint64_t first_bit;
+    load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
+    const uint32_t base = blockIdx.x * T;
+    if (base >= sh.scan_nsub) return;
+    const int tid = threadIdx.x;
+    const uint32_t lscan = base + tid;
+    SubInfo si = locate(sh, B, lscan);
+    if (tid == 0) first_bit = si.own;
+    __syncthreads();
+    load_window(sh, B, first_bit);
+    WinSrc src = win_src(sh, B);
+    const size_t g = (size_t)sh.sc.sub0 + lscan;
+    uint64_t entry = 0, ex = 0;
+    SubCount k{0, {0, 0, 0}};
+    if (si.valid) {
+        entry = B.sub_entry[g];
+        ex = B.sub_exit[g];
+        uint4 c = reinterpret_cast<const uint4*>(B.sub_count)[g];
+        k.blocks = c.x; k.dc[0] = (int)c.y; k.dc[1] = (int)c.z; k.dc[2] = (int)c.w;
+    }
+    const bool head = si.valid && si.l == 0;          // entry state known exactly
+    const bool needs_prev_cta = (tid == 0) && si.valid && !head;
+    uint32_t* my_chain = chain + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kChainWords;
+    const uint32_t* prev_chain = my_chain - kChainWords;
+    uint32_t changes = 0;
+
+    auto converge = [&]() {
+        for (;;) {
+            s_exit[tid] = ex;
+            __syncthreads();
+            int mine = 0;
+            if (si.valid && !head) {
+                uint64_t want = (tid == 0) ? s_prev_exit : s_exit[tid - 1];
+                if (entry != want) {
+                    entry = want;
+                    run_sub(sh, src, si, entry, ex, k);
+                    mine = 1;
+                    changes++;
+                }
+            }
+            if (!__syncthreads_or(mine)) break;
+        }
+    };
+
+    // 1. local convergence with the speculative entry of the CTA's first subsequence
+    if (tid == 0) s_prev_exit = entry;
+    __syncthreads();
+    converge();
+    // 2. chain: wait for the previous CTA of this scan, repair if its final exit state differs
+    if (tid == 0) {
+        uint32_t carry[4] = {0, 0, 0, 0};
+        if (needs_prev_cta) {
+            volatile const uint32_t* pc = prev_chain;
+            while (pc[6] == 0u) __nanosleep(40);
+            __threadfence();
+            s_prev_exit = (uint64_t)pc[0] | ((uint64_t)pc[1] << 32);
+            carry[0] = pc[2]; carry[1] = pc[3]; carry[2] = pc[4]; carry[3] = pc[5];
+        } else {
+            s_prev_exit = entry;
+        }
+        for (int i = 0; i < 4; i++) s_carry[i] = carry[i];
+    }
+    __syncthreads();
+    converge();
+    // 3. segmented exclusive prefix over the CTA (segments start at stream heads)
+    s_head[tid] = head ? 1u : 0u;
+    s_cnt[tid][0] = si.valid ? k.blocks : 0u;
+    s_cnt[tid][1] = si.valid ? (uint32_t)k.dc[0] : 0u;
+    s_cnt[tid][2] = si.valid ? (uint32_t)k.dc[1] : 0u;
+    s_cnt[tid][3] = si.valid ? (uint32_t)k.dc[2] : 0u;
+    if (tid == 0 && !head) {  // carry-in from the previous CTA belongs to thread 0's segment
+        for (int i = 0; i < 4; i++) s_cnt[0][i] += s_carry[i];
+    }
+    __syncthreads();
+    for (int o = 1; o < T; o <<= 1) {  // inclusive segmented scan (Hillis-Steele)
+        uint32_t a[4] = {0, 0, 0, 0};
+        uint32_t h = s_head[tid];
+        bool take = tid >= o && !h;
+        if (take) {
+            for (int i = 0; i < 4; i++) a[i] = s_cnt[tid - o][i];
+            h = s_head[tid - o];
+        }
+        __syncthreads();
+        if (take) {
+            for (int i = 0; i < 4; i++) s_cnt[tid][i] += a[i];
+            s_head[tid] = h;
+        }
+        __syncthreads();
+    }
+    if (si.valid) {
+        uint32_t own[4] = {k.blocks, (uint32_t)k.dc[0], (uint32_t)k.dc[1], (uint32_t)k.dc[2]};
+        uint4 pre = make_uint4(s_cnt[tid][0] - own[0], s_cnt[tid][1] - own[1], s_cnt[tid][2] - own[2], s_cnt[tid][3] - own[3]);
+        B.sub_entry[g] = entry;
+        B.sub_exit[g] = ex;
+        reinterpret_cast<uint4*>(B.sub_count)[g] = make_uint4(own[0], own[1], own[2], own[3]);
+        reinterpret_cast<uint4*>(B.sub_prefix)[g] = pre;
+    }
+    // 4. publish: exit state and running totals (of the stream that is open at the CTA's end)
+    uint32_t last = min((uint32_t)T, sh.scan_nsub - base) - 1;
+    if (tid == (int)last) {
+        my_chain[0] = (uint32_t)ex;
+        my_chain[1] = (uint32_t)(ex >> 32);
+        my_chain[2] = s_cnt[tid][0];
+        my_chain[3] = s_cnt[tid][1];
+        my_chain[4] = s_cnt[tid][2];
+        my_chain[5] = s_cnt[tid][3];
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(my_chain + 6) = 1u;
+    }
+    if (changes && B.sync_changes) atomicAdd(B.sync_changes, changes);
+}
+
+// ---- writing pass ------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t block_address(const bj_scan& sc, uint32_t mcu, int slot) {
+    if (sc.interleaved) return (size_t)sc.coef_block0 + (size_t)mcu * sc.frame_bpm + sc.slot_frame[slot];
+    uint32_t by = mcu / sc.mcus_x, bx = mcu - by * sc.mcus_x;
+    uint32_t fm = (by / sc.comp_v) * sc.frame_mcus_x + bx / sc.comp_h;
+    return (size_t)sc.coef_block0 + (size_t)fm * sc.frame_bpm + sc.comp_slot0 + (by % sc.comp_v) * sc.comp_h + (bx % sc.comp_h);
+}
+
+// Baseline block sink: the thread's block lives in shared memory as 8 chunks of 16 bytes, chunk c of
+// thread t at (c * T + t) * 16 (conflict-free 128-bit access across lanes); the four 32-bit words of a
+// chunk are XOR-permuted by (t >> 3) & 3 so that 16-bit stores of neighbouring lanes spread over banks.
+struct SmemBlockSink {
+    uint32_t* buf;  // T * 32 words
+    int tid;
+    int perm;
+    int16_t* coef;
+    const bj_scan* sc;
+    uint32_t mcu0;
+    __device__ __forceinline__ void begin() {}
+    __device__ __forceinline__ void put(int z, int16_t v) {
+        int chunk = z >> 3, w = ((z & 7) >> 1) ^ perm;
+        int16_t* p = reinterpret_cast<int16_t*>(buf + (chunk * T + tid) * 4 + w) + (z & 1);
+        *p = v;
+    }
+    __device__ __forceinline__ void commit(uint32_t blk, int slot) {
+        uint32_t mcu = mcu0 + blk / sc->nslots;
+        uint4* dst = reinterpret_cast<uint4*>(coef + block_address(*sc, mcu, slot) * 64);
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            uint4* s = reinterpret_cast<uint4*>(buf + (c * T + tid) * 4);
+            uint4 v = *s;
+            *s = zero;
+            if (perm & 1) { uint32_t t0 = v.x; v.x = v.y; v.y = t0; t0 = v.z; v.z = v.w; v.w = t0; }
+            if (perm & 2) { uint32_t t0 = v.x; v.x = v.z; v.z = t0; t0 = v.y; v.y = v.w; v.w = t0; }
+            dst[c] = v;
+        }
+    }
+};
+
+struct GlobalCoefSink {  // progressive first scans: single coefficient stores
+    int16_t* coef;
+    const bj_scan* sc;
+    uint32_t mcu0;
+    __device__ __forceinline__ void store_dc(uint32_t blk, int slot, int16_t v) {
+        uint32_t mcu = mcu0 + blk / sc->nslots;
+        coef[block_address(*sc, mcu, slot) * 64] = v;
+    }
+    __device__ __forceinline__ void store(uint32_t blk, int z, int16_t v) {
+        coef[block_address(*sc, mcu0 + blk, 0) * 64 + z] = v;
+    }
+};
+
+__global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
+                                                  uint32_t lut_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
+    __shared__ __align__(16) uint32_t s_blocks[T * 32];
+    __shared__ uint64_t first_bit;
+    load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
+    const uint32_t base = blockIdx.x * T;
+    if (base >= sh.scan_nsub) return;
+    const int tid = threadIdx.x;
+    const uint32_t lscan = base + tid;
+    SubInfo si = locate(sh, B, lscan);
+    if (tid == 0) first_bit = si.own;
+    for (int i = tid; i < T * 32; i += T) s_blocks[i] = 0u;
+    __syncthreads();
+    load_window(sh, B, first_bit);
+    if (!si.valid) return;
+    WinSrc src = win_src(sh, B);
+    const size_t g = (size_t)sh.sc.sub0 + lscan;
+    const uint64_t st = B.sub_entry[g];
+    const uint4 pre = reinterpret_cast<const uint4*>(B.sub_prefix)[g];
+    BitReader<WinSrc> rd;
+    rd.seek(&src, state_pos(st));
+    int z = state_z(st), slot = state_slot(st);
+    uint32_t blk = pre.x;
+    int pred[3] = {(int)pre.y, (int)pre.z, (int)pre.w};
+    uint32_t err = 0;
+    const int mode = sh.sc.mode;
+    if (mode == BJ_MODE_BASELINE) {
+        SmemBlockSink sink{s_blocks, tid, (tid >> 3) & 3, B.coef, &sh.sc, si.mcu0};
+        err = base_write_run(rd, z, slot, sh.ctx, si.stop, si.b1, blk, si.nblk_stream, pred, sink);
+    } else if (mode == BJ_MODE_DC_FIRST) {
+        GlobalCoefSink sink{B.coef, &sh.sc, si.mcu0};
+        err = dcfirst_write_run(rd, slot, sh.ctx, si.stop, si.b1, blk, si.nblk_stream, pred, sink);
+    } else {
+        GlobalCoefSink sink{B.coef, &sh.sc, si.mcu0};
+        uint32_t adv = 0;
+        err = acfirst_run<true>(rd, z, sh.ctx, si.own, si.stop, si.b1, blk, si.nblk_stream, adv, sink);
+    }
+    // the last subsequence of a stream checks that the stream held all its blocks
+    if (si.stop == si.b1) {
+        uint4 c = reinterpret_cast<const uint4*>(B.sub_count)[g];
+        if (pre.x + c.x < si.nblk_stream) err |= BJ_ERR_OVERRUN;
+    }
+    if (err) atomicOr(&B.err[sh.sc.image], err);
+}
+
+// ---- DC refinement (:1036-1043): bit b of a stream belongs to its block b -----------------------------
+__global__ void __launch_bounds__(256) dcrefine_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B) {
+    const bj_scan& sc = scans[scan_first + blockIdx.y];
+    const uint32_t total = sc.n_mcu * sc.nslots;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t mcu = i / sc.nslots;
+        int slot = (int)(i - mcu * sc.nslots);
+        uint32_t m = mcu / sc.ri;
+        uint32_t b = i - m * sc.ri * sc.nslots;
+        uint64_t bit = B.stream_start[sc.stream0 + m] * 8 + b;
+        if (bit >= B.stream_end[sc.stream0 + m] * 8) {
+            atomicOr(&B.err[sc.image], BJ_ERR_OVERRUN);
+            continue;
+        }
+        uint32_t v = (__ldg(B.words + (bit >> 5)) >> (31 - (uint32_t)(bit & 31))) & 1u;
+        int16_t* c = B.coef + block_address(sc, mcu, slot) * 64;
+        *c = (int16_t)(*c | (int16_t)(v << sc.al));
+    }
+}
+
+// ---- AC refinement: sequential per stream ---------------------------------------------------------------
+struct GlobalCoefRef {
+    int16_t* coef;
+    const bj_scan* sc;
+    uint32_t mcu0;
+    __device__ __forceinline__ int16_t& at(uint32_t blk, int z) { return coef[block_address(*sc, mcu0 + blk, 0) * 64 + z]; }
+};
+
+__global__ void __launch_bounds__(32) acrefine_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
+                                                      uint32_t lut_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
+    load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
+    const bj_scan& sc = sh.sc;
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= sc.n_streams) return;
+    GlobalSrc src{B.words, (uint32_t)B.words_len};
+    BitReader<GlobalSrc> rd;
+    rd.seek(&src, B.stream_start[sc.stream0 + m] * 8);
+    const uint32_t mcu0 = m * sc.ri;
+    const uint32_t nblk = min(sc.ri, sc.n_mcu - mcu0);
+    GlobalCoefRef cf{B.coef, &sc, mcu0};
+    uint32_t err = acrefine_stream(rd, sh.ctx, B.stream_end[sc.stream0 + m] * 8, nblk, cf);
+    if (err) atomicOr(&B.err[sc.image], err);
+}
+
+size_t cta_smem_bytes(uint32_t lut_cap) { return sizeof(CtaShared) + sizeof(uint32_t) * lut_cap; }
+
+}  // namespace
+
+extern "C" {
+
+static_assert(sizeof(bj_scan) == 144, "bj_scan layout");
+static_assert(offsetof(bj_scan, raw_len) == 16 && offsetof(bj_scan, tile0) == 60 && offsetof(bj_scan, frame_mcus_x) == 64 &&
+              offsetof(bj_scan, slot_frame) == 78 && offsetof(bj_scan, slot_comp) == 88 && offsetof(bj_scan, slot_dc) == 98 &&
+              offsetof(bj_scan, slot_ac) == 118 && offsetof(bj_scan, reserved) == 140, "bj_scan layout");
+int bj_sizeof_entropy(int what) { return what == 1 ? (int)sizeof(bj_scan) : what == 2 ? (int)sizeof(bj_entropy_buffers) : -1; }
+
+bj_status bj_entropy_plan(const bj_scan* scans, int scan_first, int n_scans, const uint64_t* tile_sum,
+                          const bj_entropy_buffers* bufs, void* stream) {
+    if (!scans || n_scans <= 0 || !tile_sum || !bufs) return BJ_E_ARG;
+    plan_kernel<<<n_scans, 256, 0, (cudaStream_t)stream>>>(scans, scan_first, tile_sum, *bufs);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_plan");
+    return BJ_OK;
+}
+
+bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, int mode, uint32_t max_sub,
+                            uint32_t max_streams, uint32_t max_blocks, uint32_t max_lut,
+                            const bj_entropy_buffers* bufs, uint32_t* chain, void* stream) {
+    if (!scans || n_scans <= 0 || n_scans > 65535 || !bufs) return BJ_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    const uint32_t lut_cap = max_lut < (uint32_t)kMaxLutSmem ? max_lut : (uint32_t)kMaxLutSmem;
+    const size_t smem = cta_smem_bytes(lut_cap);
+    if (mode == BJ_MODE_BASELINE || mode == BJ_MODE_DC_FIRST || mode == BJ_MODE_AC_FIRST) {
+        if (!chain || max_sub == 0) return BJ_E_ARG;
+        e = cudaFuncSetAttribute(spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
+        dim3 grid((max_sub + T - 1) / T, (unsigned)n_scans);
+        e = cudaMemsetAsync(chain, 0, sizeof(uint32_t) * kChainWords * (size_t)grid.x * grid.y, st);
+        if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/memset");
+        spec_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        fix_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, chain, lut_cap);
+        write_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+    } else if (mode == BJ_MODE_DC_REFINE) {
+        unsigned gx = (max_blocks + 255) / 256;
+        if (gx == 0) gx = 1;
+        if (gx > 4096) gx = 4096;
+        dcrefine_kernel<<<dim3(gx, (unsigned)n_scans), 256, 0, st>>>(scans, scan_first, *bufs);
+    } else if (mode == BJ_MODE_AC_REFINE) {
+        e = cudaFuncSetAttribute(acrefine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
+        unsigned gx = (max_streams + 31) / 32;
+        if (gx == 0) gx = 1;
+        acrefine_kernel<<<dim3(gx, (unsigned)n_scans), 32, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+    } else {
+        return BJ_E_ARG;
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/launch");
+    return BJ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// bj_entropy.cuh -- per-thread logic of the entropy stage (Huffman / run-length / progressive
+// bookkeeping), written as __host__ __device__ templates over a bit source so that the CPU test-suite
+// (tests/hostsim) can drive exactly the code the CUDA kernels in bj_entropy.cu run.
+//
+// Reference being replaced (tbpaolini/PyJpegDecoder, jpeg_decoder.py):
+//   bits_generator / get_bits   :654-695    bit reader (un-stuffing is done by bj_unstuff.cu)
+//   next_huffval                :712-722    canonical Huffman decode, <= 16 bits
+//   bin_twos_complement         :1636-1646  EXTEND
+//   baseline_dct_scan           :805-866    DC difference + AC run/size loop (EOB 0x00, ZRL 0xF0)
+//   progressive_dct_scan        :983-1057   DC first / DC refine
+//                               :1120-1256  AC first with EOB runs
+//                               :1100-1115, :1183-1198, :1209-1232, :1258-1292  AC refinement
+//
+// Parallel decomposition (new design, nothing like it exists in the reference): a stream (restart
+// interval, or a whole scan) is cut into subsequences of BJ_SUBSEQ_BITS bits.  The decoder state at
+// a subsequence boundary is (bit position, zig-zag index, slot in the MCU).  Huffman codes
+// self-synchronise: a decoder started at a wrong state falls into step with the true one after a few
+// symbols, so a speculative pass that starts one subsequence early yields, for almost every
+// subsequence, its true entry state; a fix-up pass re-decodes the few that disagree with their
+// predecessor's exit state until nothing changes (then all states are true by induction from the
+// known state at the stream start).  Prefix sums of "blocks started per subsequence" and of the DC
+// differences then give every subsequence its first block index and DC predictors, and a final
+// pass writes whole 128-byte blocks.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/b200jpeg.h"
+#include "bj_pixel_math.cuh"  // BJ_HD
+
+namespace bj {
+
+// ---- packed decoder state ------------------------------------------------------------------------
+// bits 0..43 bit position in the un-stuffed buffer, 44..50 zig-zag index, 51..54 slot.
+BJ_HD uint64_t pack_state(uint64_t pos, int z, int slot) {
+    return pos | ((uint64_t)(uint32_t)z << 44) | ((uint64_t)(uint32_t)slot << 51);
+}
+BJ_HD uint64_t state_pos(uint64_t s) { return s & ((1ull << 44) - 1); }
+BJ_HD int state_z(uint64_t s) { return (int)((s >> 44) & 127); }
+BJ_HD int state_slot(uint64_t s) { return (int)((s >> 51) & 15); }
+
+// ---- Huffman LUT entry (built by pyjpegdecoder_b200/huffman.py) ----------------------------------
+// direct:   bits 0..7 symbol, 8..12 code length L (0 = no such code), 13..17 L + (symbol & 15),
+//           18..24 zig-zag advance for baseline AC (run + 1; 64 for EOB; 16 for ZRL)
+// indirect: bit 31 set, bits 0..15 offset of a 128-entry second-level table (relative to the table)
+// first level: 512 entries indexed by the next 9 bits; second level by the following 7 bits.
+BJ_HD uint32_t lut_lookup(const uint32_t* tab, uint32_t peek16) {
+    uint32_t e = tab[peek16 >> 7];
+    if (e & 0x80000000u) e = tab[(e & 0xFFFFu) + (peek16 & 127u)];
+    return e;
+}
+BJ_HD int ent_sym(uint32_t e) { return (int)(e & 255u); }
+BJ_HD int ent_len(uint32_t e) { return (int)((e >> 8) & 31u); }
+BJ_HD int ent_total(uint32_t e) { return (int)((e >> 13) & 31u); }
+BJ_HD int ent_adv(uint32_t e) { return (int)((e >> 18) & 127u); }
+
+// EXTEND (bin_twos_complement, :1636-1646)
+BJ_HD int extend(uint32_t v, int n) { return (n == 0) ? 0 : ((v >> (n - 1)) ? (int)v : (int)v - ((1 << n) - 1)); }
+
+// ---- bit reader over big-endian 32-bit words -----------------------------------------------------
+template <class Src>
+struct BitReader {
+    const Src* src;
+    uint64_t buf;   // next bits, MSB first
+    int avail;      // valid bits in buf (> 32 between symbols)
+    uint32_t next;  // next word to fetch
+    uint64_t pos;   // absolute bit position of buf's MSB
+
+    BJ_HDM void seek(const Src* s, uint64_t p) {
+        src = s;
+        pos = p;
+        uint32_t w = (uint32_t)(p >> 5);
+        int sh = (int)(p & 31);
+        uint64_t hi = src->word(w), lo = src->word(w + 1);
+        buf = ((hi << 32) | lo) << sh;
+        avail = 64 - sh;
+        next = w + 2;
+        if (avail <= 32) {
+            buf |= (uint64_t)src->word(next++) << (32 - avail);
+            avail += 32;
+        }
+    }
+    BJ_HDM uint32_t peek16() const { return (uint32_t)(buf >> 48); }
+    // n bits (1..16) that follow the first `skipn` bits
+    BJ_HDM uint32_t bits_after(int skipn, int n) const { return (uint32_t)((buf << skipn) >> (64 - n)); }
+    BJ_HDM void skip(int n) {  // n <= 32
+        buf <<= n;
+        avail -= n;
+        pos += (uint64_t)n;
+        if (avail <= 32) {
+            buf |= (uint64_t)src->word(next++) << (32 - avail);
+            avail += 32;
+        }
+    }
+};
+
+// ---- per-scan context (shared memory on the device) ----------------------------------------------
+struct ScanCtx {
+    const uint32_t* lut;              // this scan's LUT blob
+    uint16_t dc_tab[BJ_MAX_SLOTS];    // table offsets inside the blob
+    uint16_t ac_tab[BJ_MAX_SLOTS];
+    uint8_t slot_comp[BJ_MAX_SLOTS];  // slot -> DC predictor index
+    int nslots;
+    int ss, se, al;
+};
+
+struct SubCount {
+    uint32_t blocks;  // blocks started (baseline / DC) or block advance (AC first) in the subsequence
+    int32_t dc[3];    // sum of DC differences per scan component
+};
+
+// True when the bits from pos to the end of the stream are only the 1-padding of the last byte
+// (fewer than 8 bits, all ones): no Huffman code consists of ones only, so real data never looks
+// like this.
+template <class Src>
+BJ_HD bool at_padding(const BitReader<Src>& rd, uint64_t stream_end) {
+    if (rd.pos >= stream_end) return true;
+    uint64_t left = stream_end - rd.pos;
+    if (left >= 8) return false;
+    uint32_t ones = (1u << left) - 1u;
+    return rd.bits_after(0, (int)left) == ones;
+}
+
+#define BJ_M_BASE 0
+#define BJ_M_DCFIRST 1
+
+// ---- baseline / DC-first: counting pass ----------------------------------------------------------
+// Decode from (rd.pos, z, slot) until rd.pos >= stop.  Blocks whose DC symbol starts at a position
+// >= own_start are counted and their DC differences summed.  Nothing is written.
+template <int MODE, class Src>
+BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, uint64_t own_start, uint64_t stop,
+                    uint64_t stream_end, SubCount& cnt) {
+    while (rd.pos < stop) {
+        uint32_t pk = rd.peek16();
+        if (z == 0) {
+            if (stream_end - rd.pos < 8 && at_padding(rd, stream_end)) {
+                rd.pos = stream_end;
+                break;
+            }
+            uint32_t e = lut_lookup(c.lut + c.dc_tab[slot], pk);
+            int L = ent_len(e), t = ent_sym(e), tot = ent_total(e);
+            if (L == 0) { L = 1; t = 0; tot = 1; }  // not a code: any deterministic step will do while speculating
+            if (rd.pos >= own_start) {
+                cnt.blocks++;
+                int diff = extend(t ? rd.bits_after(L, t) : 0u, t);
+                int k = c.slot_comp[slot];
+                if (k == 0) cnt.dc[0] += diff;
+                else if (k == 1) cnt.dc[1] += diff;
+                else cnt.dc[2] += diff;
+            }
+            rd.skip(tot);
+            z = (MODE == BJ_M_DCFIRST) ? 64 : 1;
+        } else {
+            uint32_t e = lut_lookup(c.lut + c.ac_tab[slot], pk);
+            int L = ent_len(e);
+            int tot = L ? ent_total(e) : 1, adv = L ? ent_adv(e) : 1;
+            rd.skip(tot);
+            z += adv;
+        }
+        if (z >= 64) {
+            z = 0;
+            slot = (slot + 1 == c.nslots) ? 0 : slot + 1;
+        }
+    }
+}
+
+// ---- baseline: writing pass ----------------------------------------------------------------------
+// Sink: begin(), put(zigzag_index, value), commit(block_in_stream) -- one whole block at a time.
+// Returns BJ_ERR_* bits.  `blk` is the index (within the stream) of the first block this thread
+// owns; on return it is one past the last block written.
+template <class Src, class Sink>
+BJ_HD uint32_t base_write_run(BitReader<Src>& rd, int z, int slot, const ScanCtx& c, uint64_t stop, uint64_t stream_end,
+                              uint32_t& blk, uint32_t nblk_stream, int pred[3], Sink& sink) {
+    // finish (without writing) the block that the previous subsequence started
+    while (z != 0) {
+        if (rd.pos >= stream_end + 64) return BJ_ERR_OVERRUN;
+        uint32_t e = lut_lookup(c.lut + c.ac_tab[slot], rd.peek16());
+        if (ent_len(e) == 0) return BJ_ERR_BAD_CODE;
+        rd.skip(ent_total(e));
+        z += ent_adv(e);
+        if (z >= 64) {
+            z = 0;
+            slot = (slot + 1 == c.nslots) ? 0 : slot + 1;
+        }
+    }
+    while (rd.pos < stop && blk < nblk_stream) {
+        sink.begin();
+        {
+            uint32_t e = lut_lookup(c.lut + c.dc_tab[slot], rd.peek16());
+            int L = ent_len(e), t = ent_sym(e);
+            if (L == 0) return BJ_ERR_BAD_CODE;
+            int diff = extend(t ? rd.bits_after(L, t) : 0u, t);
+            int k = c.slot_comp[slot];
+            int pv;
+            if (k == 0) pv = (pred[0] += diff);
+            else if (k == 1) pv = (pred[1] += diff);
+            else pv = (pred[2] += diff);
+            sink.put(0, (int16_t)pv);  // previous_dc is int16 (:735, :818-820)
+            rd.skip(ent_total(e));
+        }
+        int zz = 1;
+        while (zz < 64) {
+            uint32_t e = lut_lookup(c.lut + c.ac_tab[slot], rd.peek16());
+            int L = ent_len(e), rs = ent_sym(e);
+            if (L == 0) return BJ_ERR_BAD_CODE;
+            int s = rs & 15;
+            zz += ent_adv(e) - 1;  // zero run (EOB: jumps past 63, ZRL: 15)
+            if (zz < 64 && s) sink.put(zz, (int16_t)extend(rd.bits_after(L, s), s));
+            rd.skip(ent_total(e));
+            zz++;
+        }
+        if (rd.pos > stream_end + 7) return BJ_ERR_OVERRUN;
+        sink.commit(blk, slot);
+        blk++;
+        slot = (slot + 1 == c.nslots) ? 0 : slot + 1;
+    }
+    return 0;
+}
+
+// ---- DC first: writing pass (one 16-bit store per block) -----------------------------------------
+template <class Src, class Sink>
+BJ_HD uint32_t dcfirst_write_run(BitReader<Src>& rd, int slot, const ScanCtx& c, uint64_t stop, uint64_t stream_end,
+                                 uint32_t& blk, uint32_t nblk_stream, int pred[3], Sink& sink) {
+    while (rd.pos < stop && blk < nblk_stream) {
+        uint32_t e = lut_lookup(c.lut + c.dc_tab[slot], rd.peek16());
+        int L = ent_len(e), t = ent_sym(e);
+        if (L == 0) return BJ_ERR_BAD_CODE;
+        int diff = extend(t ? rd.bits_after(L, t) : 0u, t);
+        int k = c.slot_comp[slot];
+        int pv;
+        if (k == 0) pv = (pred[0] += diff);
+        else if (k == 1) pv = (pred[1] += diff);
+        else pv = (pred[2] += diff);
+        rd.skip(ent_total(e));
+        if (rd.pos > stream_end + 7) return BJ_ERR_OVERRUN;
+        sink.store_dc(blk, slot, (int16_t)((uint32_t)(int32_t)(int16_t)pv << c.al));  // (:1029)
+        blk++;
+        slot = (slot + 1 == c.nslots) ? 0 : slot + 1;
+    }
+    return 0;
+}
+
+// ---- AC first (:1120-1256) -----------------------------------------------------------------------
+// State: zig-zag index z in [ss, se].  A symbol either places a coefficient after a zero run, skips
+// 16 zeros (ZRL), or ends the band of this block and of the next EOBRUN-1 blocks.  WRITE = false:
+// count block advance only; WRITE = true: also store coefficients of symbols that start at or
+// after own_start (symbol-level ownership; the planes were zeroed before the first scan).
+template <bool WRITE, class Src, class Sink>
+BJ_HD uint32_t acfirst_run(BitReader<Src>& rd, int& z, const ScanCtx& c, uint64_t own_start, uint64_t stop,
+                           uint64_t stream_end, uint32_t& blk, uint32_t nblk_stream, uint32_t& advance, Sink& sink) {
+    const uint32_t* tab = c.lut + c.ac_tab[0];
+    while (rd.pos < stop) {
+        if (WRITE && blk >= nblk_stream) break;
+        if (stream_end - rd.pos < 8 && at_padding(rd, stream_end)) {
+            rd.pos = stream_end;
+            break;
+        }
+        uint32_t e = lut_lookup(tab, rd.peek16());
+        int L = ent_len(e), rs = ent_sym(e);
+        bool own = rd.pos >= own_start;
+        if (L == 0) {
+            if (WRITE) return BJ_ERR_BAD_CODE;
+            rd.skip(1);
+            continue;
+        }
+        int r = rs >> 4, s = rs & 15;
+        uint32_t adv = 0;
+        if (s) {
+            z += r;
+            if (WRITE && own) {
+                if (z > 63) return BJ_ERR_COEF_INDEX;
+                sink.store(blk, z, (int16_t)((uint32_t)extend(rd.bits_after(L, s), s) << c.al));  // (:1225)
+            }
+            z++;
+            rd.skip(L + s);
+        } else if (r == 15) {
+            z += 16;  // (:1142-1143)
+            rd.skip(L);
+        } else {
+            uint32_t run = (1u << r) + (r ? rd.bits_after(L, r) : 0u);  // (:1144-1149)
+            rd.skip(L + r);
+            adv = run;
+            z = c.ss;
+        }
+        if (z > c.se) {
+            adv = 1;
+            z = c.ss;
+        }
+        blk += adv;
+        if (own) advance += adv;
+    }
+    return 0;
+}
+
+// ---- AC refinement (:1100-1115, :1183-1198, :1209-1232, :1258-1292) -------------------------------
+// Sequential over one stream: the number of correction bits after a symbol depends on which
+// coefficients of the block are already non-zero.  Coef: at(block_in_stream, zigzag) -> int16_t&.
+// Correction is the reference's `coef |= bit << Al` on the two's-complement value (:1114), which is
+// NOT the T.81 rule for negative coefficients; bit-exact parity with the reference requires it.
+template <class Src, class Coef>
+BJ_HD uint32_t acrefine_stream(BitReader<Src>& rd, const ScanCtx& c, uint64_t stream_end, uint32_t nblk_stream, Coef& coef) {
+    const uint32_t* tab = c.lut + c.ac_tab[0];
+    const int ss = c.ss, se = c.se, al = c.al;
+    uint32_t blk = 0;
+    while (blk < nblk_stream) {
+        int z = ss;
+        uint32_t eob_run = 0;
+        while (z <= se) {
+            if (rd.pos > stream_end + 7) return BJ_ERR_OVERRUN;
+            uint32_t e = lut_lookup(tab, rd.peek16());
+            int L = ent_len(e), rs = ent_sym(e);
+            if (L == 0) return BJ_ERR_BAD_CODE;
+            int r = rs >> 4, s = rs & 15;
+            int zero_run;
+            int newval = 0;
+            if (rs == 0) {
+                rd.skip(L);
+                eob_run = 1;
+                break;
+            } else if (rs == 0xF0) {
+                rd.skip(L);
+                zero_run = 16;
+            } else if (s == 0) {
+                eob_run = (1u << r) + (r ? rd.bits_after(L, r) : 0u);
+                rd.skip(L + r);
+                break;
+            } else {
+                zero_run = r;
+                newval = extend(rd.bits_after(L, s), s);  // value bits come right after the code (:1202)
+                rd.skip(L + s);
+            }
+            // skip `zero_run` zero-history coefficients, refining the non-zero ones passed (:1184-1193);
+            // their correction bits follow in the same order (:1107-1115)
+            while (zero_run > 0) {
+                if (z > 63) return BJ_ERR_COEF_INDEX;
+                int16_t& cf = coef.at(blk, z);
+                if (cf == 0) zero_run--;
+                else {
+                    cf = (int16_t)(cf | (int16_t)(rd.bits_after(0, 1) << al));
+                    rd.skip(1);
+                }
+                z++;
+            }
+            if (s) {
+                // a new coefficient lands on the next zero-history position (:1211-1215)
+                for (;;) {
+                    if (z > 63) return BJ_ERR_COEF_INDEX;
+                    int16_t& cf = coef.at(blk, z);
+                    if (cf == 0) break;
+                    cf = (int16_t)(cf | (int16_t)(rd.bits_after(0, 1) << al));
+                    rd.skip(1);
+                    z++;
+                }
+                coef.at(blk, z) = (int16_t)((uint32_t)newval << al);  // (:1225)
+                z++;
+            }
+        }
+        if (z > se) {
+            blk++;
+            continue;
+        }
+        // end-of-band run: the rest of this band and the bands of the next eob_run-1 blocks only
+        // carry correction bits for their non-zero coefficients (:1258-1292)
+        while (eob_run > 0 && blk < nblk_stream) {
+            for (; z <= se; z++) {
+                int16_t& cf = coef.at(blk, z);
+                if (cf != 0) {
+                    if (rd.pos > stream_end + 7) return BJ_ERR_OVERRUN;
+                    cf = (int16_t)(cf | (int16_t)(rd.bits_after(0, 1) << al));
+                    rd.skip(1);
+                }
+            }
+            eob_run--;
+            blk++;
+            z = ss;
+        }
+    }
+    return 0;
+}
+
+}  // namespace bj

@@ -17,8 +17,10 @@
 
 #if defined(__CUDACC__)
 #define BJ_HD __host__ __device__ __forceinline__
+#define BJ_HDM __host__ __device__ __forceinline__  // member functions
 #else
 #define BJ_HD static inline
+#define BJ_HDM inline
 #endif
 
 namespace bj {

@@ -1,0 +1,128 @@
+"""Drop-in entry point: same class name, constructor and result attributes as the reference's
+JpegDecoder (jpeg_decoder.py:27-110), decoding on a B200 through libb200jpeg.so.
+
+Differences by design: never opens a GUI (the reference calls self.show() at :1389), prints nothing
+unless verbose=True, accepts str / bytes / Path, and keeps the pixels on the device until
+`image_array` is read.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .huffman import canonical_codes
+from .layout import ZIGZAG_UV
+from .parser import ParsedJpeg, parse_jpeg
+from .pipeline import DecodedBatch, decode_batch_on_device, pack_files
+
+# containers of the reference (:24-25)
+ColorComponent = namedtuple("ColorComponent", "name order vertical_sampling horizontal_sampling quantization_table_id repeat shape")
+HuffmanTable = namedtuple("HuffmanTable", "dc ac")
+
+_NAMES = ("Y", "Cb", "Cr")
+
+
+def _read(file: Union[str, Path, bytes, bytearray, memoryview]) -> bytes:
+    if isinstance(file, (bytes, bytearray, memoryview)):
+        return bytes(file)
+    with open(file, "rb") as f:
+        return f.read()
+
+
+class JpegDecoder:
+    """JpegDecoder(file) decodes in the constructor, like the reference (:29-110).
+
+    Result attributes mirror the reference: image_array (uint8, (width, height, 3) or (width, height)),
+    image_width, image_height, scan_mode, color_components, sample_shape, huffman_tables,
+    quantization_tables, restart_interval, scan_count, scan_amount, array_width/height/depth,
+    file_size, file_path.  `image_tensor` is the device tensor in (H, W, 3) layout.
+    """
+
+    def __init__(self, file: Union[str, Path, bytes], device: Optional[Union[str, torch.device]] = None,
+                 verbose: bool = False, parsed: Optional[ParsedJpeg] = None, _batch: Optional[DecodedBatch] = None,
+                 _index: int = 0):
+        if isinstance(file, (bytes, bytearray, memoryview)):
+            self.file_path = None
+            data = bytes(file)
+        else:
+            self.file_path = file if isinstance(file, Path) else Path(file)
+            data = _read(file) if _batch is None else b""
+        self.file_size = len(data) if _batch is None else _batch.plan.parsed[_index].file_size
+        if _batch is None:
+            p = parsed if parsed is not None else parse_jpeg(data)
+            _batch = decode_batch_on_device([data], device=device, parsed=[p])
+            _index = 0
+        self._batch = _batch
+        self._index = _index
+        p = _batch.plan.parsed[_index]
+        self._parsed = p
+        self.scan_finished = p.finished
+        self.scan_mode = "progressive_dct" if p.progressive else "baseline_dct"
+        self.image_width = p.width
+        self.image_height = p.height
+        self.color_components = {
+            c.id: ColorComponent(name=_NAMES[c.order], order=c.order, vertical_sampling=c.v, horizontal_sampling=c.h,
+                                 quantization_table_id=c.tq, repeat=c.h * c.v, shape=(8 * c.h, 8 * c.v))
+            for c in p.components}
+        self.sample_shape = (8 * p.hmax, 8 * p.vmax)
+        self.restart_interval = p.restart_interval
+        self.scan_count = len(p.scans)
+        self.scan_amount = p.scan_amount
+        self.array_width, self.array_height = p.canvas_size
+        self.array_depth = p.ncomp
+        last = p.scans[-1]
+        self.mcu_count_h, self.mcu_count_v = last.mcus_x, last.mcus_y
+        self.mcu_count = last.mcus_x * last.mcus_y
+        self._image_array = None
+        if verbose:
+            print(f"Decoded {self.image_width} x {self.image_height} {self.scan_mode} image, {self.scan_count} scan(s)")
+
+    # ---- pixels ----------------------------------------------------------------------------------
+    @property
+    def image_tensor(self) -> torch.Tensor:
+        """(H, W, 3) or (H, W) uint8 tensor on the device."""
+        return self._batch.images[self._index]
+
+    @property
+    def image_array(self) -> np.ndarray:
+        """uint8 numpy array shaped like the reference's: (width, height, 3) or (width, height)
+        (x-major, jpeg_decoder.py:626, :1373-1386); a transposed view of the (H, W, 3) buffer."""
+        if self._image_array is None:
+            self._image_array = np.swapaxes(self.image_tensor.cpu().numpy(), 0, 1)
+        return self._image_array
+
+    # ---- tables, in the reference's formats --------------------------------------------------------
+    @property
+    def quantization_tables(self) -> Dict[int, np.ndarray]:
+        """{table id: 8x8 int16 indexed [x, y]} as define_quantization_table stores them (:454-462)."""
+        out = {}
+        for k, q in self._parsed.qtables.items():
+            t = np.zeros((8, 8), np.int16)
+            for i, (u, v) in enumerate(ZIGZAG_UV):
+                t[u, v] = q[i]
+            out[k] = t
+        return out
+
+    @property
+    def huffman_tables(self) -> Dict[int, Dict[str, int]]:
+        """{Tc/Th byte: {bit string: symbol}} as define_huffman_table builds them (:366-377)."""
+        out = {}
+        for dest, spec in self._parsed.huff_specs.items():
+            out[dest] = {bin(code)[2:].rjust(length, "0"): sym for (code, length, sym) in canonical_codes(spec)}
+        return out
+
+    def coefficient_planes(self) -> List[np.ndarray]:
+        """Quantised DCT coefficients per component, (blocks_v, blocks_h, 64) int16 in zig-zag order."""
+        return self._batch.coefficient_grids(self._index)
+
+
+def decode_batch(files: Sequence[Union[str, Path, bytes]], device: Optional[Union[str, torch.device]] = None) -> List[JpegDecoder]:
+    """Decode many files in one device pipeline (one launch sequence for the whole batch) and return
+    one JpegDecoder-like object per file."""
+    datas = [_read(f) for f in files]
+    batch = decode_batch_on_device(datas, device=device)
+    return [JpegDecoder(f, _batch=batch, _index=i) for i, f in enumerate(files)]

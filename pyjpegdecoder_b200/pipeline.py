@@ -1,0 +1,307 @@
+"""Device pipeline for a batch of JPEG files on ONE GPU.
+
+host parse (parser.py)  ->  H2D of the file bytes  ->  bj_unstuff  ->  bj_entropy_plan  ->
+bj_entropy_decode per wave/mode  ->  bj_pixels  ->  per-image (H, W, 3) uint8 views.
+
+This is the launch site that replaces the reference's start_of_scan -> baseline_dct_scan /
+progressive_dct_scan -> end_of_image chain (jpeg_decoder.py:640-650, :1368-1388): the host records a
+scan descriptor per SOS and defers; the whole batch then runs as a handful of kernel launches.
+torch tensors are used as device buffers only; all compute is in libb200jpeg.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+from .errors import CorruptedJpeg, NativeLibraryError
+from .huffman import build_scan_blob
+from .layout import slot0_of
+from .parser import ParsedJpeg, Scan, parse_jpeg
+from .plan import BatchGeometry
+from .stages import DeviceGeometry, image_views, require_cuda, run_pixels, to_device
+
+SUBSEQ_BITS = 1024
+ENTROPY_THREADS = 128
+UNSTUFF_TILE = 4096
+MAX_SLOTS = 10
+
+MODES = {"baseline": 0, "dc_first": 1, "dc_refine": 2, "ac_first": 3, "ac_refine": 4}
+
+# numpy mirror of struct bj_scan (144 bytes, see include/b200jpeg.h)
+SCAN_DTYPE = np.dtype({
+    "names": ["raw_off", "coef_block0", "raw_len", "image", "stream0", "n_streams", "ri", "n_mcu", "mcus_x",
+              "sub0", "n_sub_max", "lut_off", "lut_len", "tile0", "frame_mcus_x", "frame_bpm", "nslots", "mode",
+              "ss", "se", "ah", "al", "interleaved", "comp_h", "comp_v", "comp_slot0", "ncomp_scan",
+              "slot_frame", "slot_comp", "slot_dc", "slot_ac", "reserved"],
+    "formats": ["<u8", "<u8", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4",
+                "<u2", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1",
+                ("u1", (MAX_SLOTS,)), ("u1", (MAX_SLOTS,)), ("<u2", (MAX_SLOTS,)), ("<u2", (MAX_SLOTS,)), "<u4"],
+    "offsets": [0, 8, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 66, 67, 68, 69, 70, 71, 72, 73, 74, 75,
+                76, 77, 78, 88, 98, 118, 140],
+    "itemsize": 144,
+})
+
+
+class EntropyBuffers(ctypes.Structure):
+    """struct bj_entropy_buffers"""
+    _fields_ = [("words", ctypes.c_void_p), ("words_len", ctypes.c_uint64),
+                ("stream_start", ctypes.c_void_p), ("stream_end", ctypes.c_void_p), ("stream_sub", ctypes.c_void_p),
+                ("sub_entry", ctypes.c_void_p), ("sub_exit", ctypes.c_void_p),
+                ("sub_count", ctypes.c_void_p), ("sub_prefix", ctypes.c_void_p),
+                ("lut", ctypes.c_void_p), ("coef", ctypes.c_void_p), ("err", ctypes.c_void_p),
+                ("sync_changes", ctypes.c_void_p)]
+
+
+_BOUND = False
+
+
+def _bind():
+    global _BOUND
+    L = _native.lib()
+    if not _BOUND:
+        vp, ci, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32
+        L.bj_sizeof_entropy.restype = ci
+        L.bj_sizeof_entropy.argtypes = [ci]
+        L.bj_unstuff.restype = ci
+        L.bj_unstuff.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp, vp, ci, vp]
+        L.bj_entropy_plan.restype = ci
+        L.bj_entropy_plan.argtypes = [vp, ci, ci, vp, ctypes.POINTER(EntropyBuffers), vp]
+        L.bj_entropy_decode.restype = ci
+        L.bj_entropy_decode.argtypes = [vp, ci, ci, ci, u32, u32, u32, u32, ctypes.POINTER(EntropyBuffers), vp, vp]
+        if L.bj_sizeof_entropy(1) != SCAN_DTYPE.itemsize or L.bj_sizeof_entropy(2) != ctypes.sizeof(EntropyBuffers):
+            raise NativeLibraryError("struct bj_scan / bj_entropy_buffers layout mismatch")
+        _BOUND = True
+    return L
+
+
+@dataclass
+class ScanGroup:
+    first: int
+    count: int
+    mode: int
+    max_sub: int
+    max_streams: int
+    max_blocks: int
+    max_lut: int
+
+
+class BatchPlan:
+    """Everything the host must compute for one batch: geometry, scan descriptors grouped into waves,
+    tile table, Huffman LUT blob, buffer sizes.  `offsets[i]` is where file i starts in the raw buffer."""
+
+    def __init__(self, parsed: Sequence[ParsedJpeg], offsets: Sequence[int], raw_bytes: int):
+        self.parsed = list(parsed)
+        self.geom = BatchGeometry(self.parsed)
+        self.raw_bytes = raw_bytes
+        n_scans = sum(len(p.scans) for p in self.parsed)
+        self.scans = np.zeros(n_scans, dtype=SCAN_DTYPE)
+        self.any_progressive = any(p.progressive for p in self.parsed)
+        lut_parts: List[np.ndarray] = []
+        lut_cache: Dict[tuple, Tuple[int, int, list, list]] = {}
+        lut_size = 0
+        # order: wave by wave (k-th scan of every image), inside a wave grouped by mode
+        order: List[Tuple[int, int, int]] = []  # (wave, mode, image, scan idx)
+        max_waves = max(len(p.scans) for p in self.parsed)
+        for w in range(max_waves):
+            items = [(MODES[p.scans[w].kind], i) for i, p in enumerate(self.parsed) if len(p.scans) > w]
+            items.sort()
+            order.extend((w, m, i) for (m, i) in items)
+        self.groups: List[ScanGroup] = []
+        stream0 = 0
+        sub0 = 0
+        tile0 = 0
+        tile_counts = []
+        cur_key = None
+        for k, (w, mode, i) in enumerate(order):
+            p = self.parsed[i]
+            sc: Scan = p.scans[w]
+            rec = self.scans[k]
+            raw_off = offsets[i] + sc.data_start
+            raw_len = sc.data_end - sc.data_start
+            n_mcu = sc.mcus_x * sc.mcus_y
+            ri = sc.ri if sc.ri > 0 else n_mcu
+            n_streams = -(-n_mcu // ri)
+            interleaved = len(sc.comps) > 1 or p.ncomp == 1
+            key = (sc.dc_specs, sc.ac_specs)
+            if key not in lut_cache:
+                blob, dc_off, ac_off = build_scan_blob(sc.dc_specs, sc.ac_specs)
+                lut_cache[key] = (lut_size, len(blob), dc_off, ac_off)
+                lut_parts.append(blob)
+                lut_size += len(blob)
+            lut_off, lut_len, dc_off, ac_off = lut_cache[key]
+            s0 = slot0_of(p)
+            slot = 0
+            for kk, ci in enumerate(sc.comps):
+                c = p.components[ci]
+                nb = c.h * c.v if len(sc.comps) > 1 else 1
+                for r in range(nb):
+                    rec["slot_frame"][slot] = s0[ci] + r
+                    rec["slot_comp"][slot] = kk
+                    rec["slot_dc"][slot] = dc_off[kk]
+                    rec["slot_ac"][slot] = ac_off[kk]
+                    slot += 1
+            if slot > MAX_SLOTS:
+                raise CorruptedJpeg("More than 10 blocks per MCU.")
+            c0 = p.components[sc.comps[0]]
+            n_sub_max = -(-raw_len * 8 // SUBSEQ_BITS) + n_streams
+            lead = raw_off & 15
+            n_tiles = max(1, -(-(lead + raw_len) // UNSTUFF_TILE))
+            rec["raw_off"], rec["raw_len"] = raw_off, raw_len
+            rec["coef_block0"] = self.geom.block_offsets[i]
+            rec["image"] = i
+            rec["stream0"], rec["n_streams"], rec["ri"], rec["n_mcu"], rec["mcus_x"] = stream0, n_streams, ri, n_mcu, sc.mcus_x
+            rec["sub0"], rec["n_sub_max"] = sub0, n_sub_max
+            rec["lut_off"], rec["lut_len"] = lut_off, lut_len
+            rec["tile0"] = tile0
+            rec["frame_mcus_x"], rec["frame_bpm"] = p.mcus_x, p.blocks_per_mcu
+            rec["nslots"], rec["mode"] = slot, mode
+            rec["ss"], rec["se"], rec["ah"], rec["al"] = sc.ss, sc.se, sc.ah, sc.al
+            rec["interleaved"] = 1 if interleaved else 0
+            rec["comp_h"], rec["comp_v"], rec["comp_slot0"] = c0.h, c0.v, s0[sc.comps[0]]
+            rec["ncomp_scan"] = len(sc.comps)
+            if (w, mode) != cur_key:
+                self.groups.append(ScanGroup(first=k, count=0, mode=mode, max_sub=0, max_streams=0, max_blocks=0, max_lut=0))
+                cur_key = (w, mode)
+            g = self.groups[-1]
+            g.count += 1
+            g.max_sub = max(g.max_sub, n_sub_max)
+            g.max_streams = max(g.max_streams, n_streams)
+            g.max_blocks = max(g.max_blocks, n_mcu * slot)
+            g.max_lut = max(g.max_lut, lut_len)
+            stream0 += n_streams
+            sub0 += n_sub_max
+            tile0 += n_tiles
+            tile_counts.append(n_tiles)
+        self.n_streams = stream0
+        self.n_sub = sub0
+        self.n_tiles = tile0
+        self.tile_scan = np.repeat(np.arange(n_scans, dtype=np.uint32), tile_counts)
+        self.lut = np.concatenate(lut_parts).astype(np.uint32)
+        self.max_chain = max((-(-g.max_sub // ENTROPY_THREADS)) * g.count for g in self.groups
+                             if g.mode in (0, 1, 3)) if any(g.mode in (0, 1, 3) for g in self.groups) else 1
+
+
+def pack_files(datas: Sequence[bytes], pin: bool = True) -> Tuple[torch.Tensor, List[int]]:
+    """Concatenate file images into one (pinned) host buffer, each file 16-byte aligned."""
+    offsets, total = [], 0
+    for d in datas:
+        offsets.append(total)
+        total += (len(d) + 15) & ~15
+    total += 64
+    buf = torch.empty(total, dtype=torch.uint8, pin_memory=pin and torch.cuda.is_available())
+    view = buf.numpy()
+    for d, off in zip(datas, offsets):
+        view[off:off + len(d)] = np.frombuffer(d, dtype=np.uint8)
+    return buf, offsets
+
+
+class DecodedBatch:
+    """Result of decoding a batch on one device."""
+
+    def __init__(self, plan: BatchPlan, out: torch.Tensor, coef: torch.Tensor, err: torch.Tensor, stats: dict):
+        self.plan = plan
+        self.out = out
+        self.coef = coef
+        self.err = err
+        self.stats = stats
+        self.images = image_views(plan.geom, out)   # (H, W, 3) / (H, W) uint8 device tensors
+
+    def image_array(self, i: int) -> torch.Tensor:
+        """The reference's layout: (W, H, 3) or (W, H) view (jpeg_decoder.py:626, :1373-1386)."""
+        return self.images[i].transpose(0, 1)
+
+    def coefficient_grids(self, i: int) -> List[np.ndarray]:
+        from .layout import device_to_grids, total_blocks
+        p = self.plan.parsed[i]
+        b0 = self.plan.geom.block_offsets[i]
+        buf = self.coef[b0:b0 + total_blocks(p)].cpu().numpy()
+        return device_to_grids(p, buf)
+
+
+def raise_for_errors(err_words: np.ndarray) -> None:
+    """Map device error words to the reference's exception classes (jpeg_decoder.py:1714-1725)."""
+    bad = np.nonzero(err_words)[0]
+    if len(bad) == 0:
+        return
+    i = int(bad[0])
+    e = int(err_words[i])
+    if e & _native.ERR_BAD_CODE:
+        raise CorruptedJpeg(f"Failed to decode image {i} (no Huffman code matches the data).")       # :718-719
+    if e & (_native.ERR_OVERRUN | _native.ERR_RST_COUNT | _native.ERR_COEF_INDEX):
+        raise CorruptedJpeg(f"Failed to decode image {i} (entropy-coded data ended early or is inconsistent).")
+    raise NativeLibraryError(f"image {i}: device decode error {e:#x}")
+
+
+def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed: Optional[Sequence[ParsedJpeg]] = None,
+                           packed: Optional[Tuple[torch.Tensor, List[int]]] = None, check: bool = True,
+                           stream: Optional[torch.cuda.Stream] = None, upto_wave: Optional[int] = None,
+                           plan: Optional[BatchPlan] = None, out_kind: int = _native.OUT_RGB) -> DecodedBatch:
+    """Decode a batch of JPEG file images on one GPU.  Returns device tensors; with check=True the
+    per-image error words are read back (one synchronisation) and turned into exceptions."""
+    dev = require_cuda(device)
+    L = _bind()
+    if packed is None:
+        packed = pack_files(datas)
+    raw_host, offsets = packed
+    if plan is None:
+        if parsed is None:
+            parsed = [parse_jpeg(d) for d in datas]
+        plan = BatchPlan(parsed, offsets, raw_host.numel())
+    g = plan.geom
+    with torch.cuda.device(dev):
+        s = stream if stream is not None else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(s):
+            raw = raw_host.to(dev, non_blocking=True)
+            scans = to_device(plan.scans, dev, non_blocking=True)
+            tile_scan = to_device(plan.tile_scan, dev, non_blocking=True)
+            lut = torch.from_numpy(plan.lut.view(np.int32)).to(dev, non_blocking=True)
+            dg = DeviceGeometry(g, dev)
+            words_len = raw_host.numel() // 4 + 64
+            words = torch.empty(words_len, dtype=torch.int32, device=dev)
+            tile_sum = torch.empty(plan.n_tiles + 1, dtype=torch.int64, device=dev)
+            stream_start = torch.empty(plan.n_streams, dtype=torch.int64, device=dev)
+            stream_end = torch.empty(plan.n_streams, dtype=torch.int64, device=dev)
+            stream_sub = torch.empty(plan.n_streams, dtype=torch.int32, device=dev)
+            n_sub = max(plan.n_sub, 1)
+            sub_entry = torch.empty(n_sub, dtype=torch.int64, device=dev)
+            sub_exit = torch.empty(n_sub, dtype=torch.int64, device=dev)
+            sub_count = torch.empty(n_sub * 4, dtype=torch.int32, device=dev)
+            sub_prefix = torch.empty(n_sub * 4, dtype=torch.int32, device=dev)
+            chain = torch.empty(plan.max_chain * 8, dtype=torch.int32, device=dev)
+            if plan.any_progressive:
+                coef = torch.zeros((g.total_blocks, 64), dtype=torch.int16, device=dev)
+            else:
+                coef = torch.empty((g.total_blocks, 64), dtype=torch.int16, device=dev)
+            err = torch.zeros(len(plan.parsed), dtype=torch.int32, device=dev)
+            sync_changes = torch.zeros(1, dtype=torch.int32, device=dev)
+            B = EntropyBuffers(words.data_ptr(), words_len, stream_start.data_ptr(), stream_end.data_ptr(),
+                               stream_sub.data_ptr(), sub_entry.data_ptr(), sub_exit.data_ptr(),
+                               sub_count.data_ptr(), sub_prefix.data_ptr(), lut.data_ptr(), coef.data_ptr(),
+                               err.data_ptr(), sync_changes.data_ptr())
+            cs = s.cuda_stream
+            _native.check(L.bj_unstuff(raw.data_ptr(), scans.data_ptr(), len(plan.scans), tile_scan.data_ptr(),
+                                       plan.n_tiles, tile_sum.data_ptr(), words.data_ptr(), stream_start.data_ptr(),
+                                       stream_end.data_ptr(), plan.n_streams, cs), "bj_unstuff")
+            _native.check(L.bj_entropy_plan(scans.data_ptr(), 0, len(plan.scans), tile_sum.data_ptr(),
+                                            ctypes.byref(B), cs), "bj_entropy_plan")
+            for gi, grp in enumerate(plan.groups):
+                if upto_wave is not None and gi >= upto_wave:
+                    break
+                _native.check(L.bj_entropy_decode(scans.data_ptr(), grp.first, grp.count, grp.mode, grp.max_sub,
+                                                  grp.max_streams, grp.max_blocks, grp.max_lut, ctypes.byref(B),
+                                                  chain.data_ptr(), cs), "bj_entropy_decode")
+            out = run_pixels(dg, coef, _native.IN_COEF, out_kind, stream=s)
+            # keep the temporaries alive until the stream has consumed them
+            keep = (raw, scans, tile_scan, lut, words, tile_sum, stream_start, stream_end, stream_sub, sub_entry,
+                    sub_exit, sub_count, sub_prefix, chain, dg)
+            for t in keep[:-1]:
+                t.record_stream(s)
+    res = DecodedBatch(plan, out, coef, err, {"sync_changes": sync_changes, "_keep": keep})
+    if check:
+        raise_for_errors(err.cpu().numpy())
+    return res
