@@ -189,10 +189,16 @@ bj_status bj_entropy_plan(const bj_scan* scans, int scan_first, int n_scans, con
  *   max_blocks   max over the wave's scans of n_mcu * nslots    (DC refine)
  *   max_lut      max over the wave's scans of lut_len
  *   chain        workspace, uint32[8 * ceil(max_sub / BJ_ENTROPY_THREADS) * n_scans]
+ *   phases       BJ_PHASE_ALL, or a subset of the three kernels of the speculative modes so that a
+ *                caller can time them separately (they must still run in this order)
  */
+#define BJ_PHASE_SPEC 1
+#define BJ_PHASE_FIX 2
+#define BJ_PHASE_WRITE 4
+#define BJ_PHASE_ALL 7
 bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, int mode, uint32_t max_sub,
                             uint32_t max_streams, uint32_t max_blocks, uint32_t max_lut,
-                            const bj_entropy_buffers* bufs, uint32_t* chain, void* stream);
+                            const bj_entropy_buffers* bufs, uint32_t* chain, int phases, void* stream);
 
 /* Output selector of bj_pixels(). */
 #define BJ_OUT_RGB 0     /* uint8: fused IDCT + upsample + YCbCr->RGB (+ clamp)            */

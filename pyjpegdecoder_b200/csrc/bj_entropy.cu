@@ -550,7 +550,7 @@ bj_status bj_entropy_plan(const bj_scan* scans, int scan_first, int n_scans, con
 
 bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, int mode, uint32_t max_sub,
                             uint32_t max_streams, uint32_t max_blocks, uint32_t max_lut,
-                            const bj_entropy_buffers* bufs, uint32_t* chain, void* stream) {
+                            const bj_entropy_buffers* bufs, uint32_t* chain, int phases, void* stream) {
     if (!scans || n_scans <= 0 || n_scans > 65535 || !bufs) return BJ_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
@@ -563,11 +563,13 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         if (e == cudaSuccess) e = cudaFuncSetAttribute(write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
         dim3 grid((max_sub + T - 1) / T, (unsigned)n_scans);
-        e = cudaMemsetAsync(chain, 0, sizeof(uint32_t) * kChainWords * (size_t)grid.x * grid.y, st);
-        if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/memset");
-        spec_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
-        fix_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, chain, lut_cap);
-        write_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        if (phases & BJ_PHASE_SPEC) spec_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        if (phases & BJ_PHASE_FIX) {
+            e = cudaMemsetAsync(chain, 0, sizeof(uint32_t) * kChainWords * (size_t)grid.x * grid.y, st);
+            if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/memset");
+            fix_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, chain, lut_cap);
+        }
+        if (phases & BJ_PHASE_WRITE) write_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
     } else if (mode == BJ_MODE_DC_REFINE) {
         unsigned gx = (max_blocks + 255) / 256;
         if (gx == 0) gx = 1;

@@ -72,7 +72,7 @@ def _bind():
         L.bj_entropy_plan.restype = ci
         L.bj_entropy_plan.argtypes = [vp, ci, ci, vp, ctypes.POINTER(EntropyBuffers), vp]
         L.bj_entropy_decode.restype = ci
-        L.bj_entropy_decode.argtypes = [vp, ci, ci, ci, u32, u32, u32, u32, ctypes.POINTER(EntropyBuffers), vp, vp]
+        L.bj_entropy_decode.argtypes = [vp, ci, ci, ci, u32, u32, u32, u32, ctypes.POINTER(EntropyBuffers), vp, ci, vp]
         if L.bj_sizeof_entropy(1) != SCAN_DTYPE.itemsize or L.bj_sizeof_entropy(2) != ctypes.sizeof(EntropyBuffers):
             raise NativeLibraryError("struct bj_scan / bj_entropy_buffers layout mismatch")
         _BOUND = True
@@ -237,14 +237,137 @@ def raise_for_errors(err_words: np.ndarray) -> None:
     raise NativeLibraryError(f"image {i}: device decode error {e:#x}")
 
 
+class DevicePipeline:
+    """Device buffers + launch sequence for one BatchPlan on one GPU.  Buffers are allocated once and
+    can be reused for any number of batches with the same plan (bench.py does that); `upload` moves
+    the file bytes, `launch` enqueues every kernel on the stream."""
+
+    STAGES = ("unstuff", "plan", "spec", "fix", "write", "other_scans", "pixels")
+
+    def __init__(self, plan: BatchPlan, device=None, stream: Optional[torch.cuda.Stream] = None):
+        self.plan = plan
+        self.dev = require_cuda(device)
+        self.L = _bind()
+        g = plan.geom
+        dev = self.dev
+        with torch.cuda.device(dev):
+            self.stream = stream if stream is not None else torch.cuda.current_stream(dev)
+            with torch.cuda.stream(self.stream):
+                self.scans = to_device(plan.scans, dev)
+                self.tile_scan = to_device(plan.tile_scan, dev)
+                self.lut = torch.from_numpy(plan.lut.view(np.int32)).to(dev)
+                self.dg = DeviceGeometry(g, dev)
+                self.raw = torch.empty(plan.raw_bytes, dtype=torch.uint8, device=dev)
+                self.words_len = plan.raw_bytes // 4 + 64
+                self.words = torch.empty(self.words_len, dtype=torch.int32, device=dev)
+                self.tile_sum = torch.empty(plan.n_tiles + 1, dtype=torch.int64, device=dev)
+                self.stream_start = torch.empty(plan.n_streams, dtype=torch.int64, device=dev)
+                self.stream_end = torch.empty(plan.n_streams, dtype=torch.int64, device=dev)
+                self.stream_sub = torch.empty(plan.n_streams, dtype=torch.int32, device=dev)
+                n_sub = max(plan.n_sub, 1)
+                self.sub_entry = torch.empty(n_sub, dtype=torch.int64, device=dev)
+                self.sub_exit = torch.empty(n_sub, dtype=torch.int64, device=dev)
+                self.sub_count = torch.empty(n_sub * 4, dtype=torch.int32, device=dev)
+                self.sub_prefix = torch.empty(n_sub * 4, dtype=torch.int32, device=dev)
+                self.chain = torch.empty(plan.max_chain * 8, dtype=torch.int32, device=dev)
+                self.coef = torch.empty((g.total_blocks, 64), dtype=torch.int16, device=dev)
+                self.err = torch.zeros(len(plan.parsed), dtype=torch.int32, device=dev)
+                self.sync_changes = torch.zeros(1, dtype=torch.int32, device=dev)
+                self.out = None
+        self.B = EntropyBuffers(self.words.data_ptr(), self.words_len, self.stream_start.data_ptr(),
+                                self.stream_end.data_ptr(), self.stream_sub.data_ptr(), self.sub_entry.data_ptr(),
+                                self.sub_exit.data_ptr(), self.sub_count.data_ptr(), self.sub_prefix.data_ptr(),
+                                self.lut.data_ptr(), self.coef.data_ptr(), self.err.data_ptr(),
+                                self.sync_changes.data_ptr())
+        self.kernel_launches_per_step = 0
+
+    def device_bytes(self) -> int:
+        ts = [self.scans, self.tile_scan, self.lut, self.raw, self.words, self.tile_sum, self.stream_start,
+              self.stream_end, self.stream_sub, self.sub_entry, self.sub_exit, self.sub_count, self.sub_prefix,
+              self.chain, self.coef, self.err]
+        return sum(t.numel() * t.element_size() for t in ts) + self.plan.geom.out_bytes
+
+    def upload(self, raw_host: torch.Tensor) -> None:
+        """H2D of the packed file bytes (async on the pipeline's stream when raw_host is pinned)."""
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+            self.raw.copy_(raw_host, non_blocking=True)
+
+    def launch(self, out_kind: int = _native.OUT_RGB, upto_group: Optional[int] = None, events: Optional[dict] = None):
+        """Enqueue un-stuffing, entropy decode and the pixel kernel.  With `events` (a dict), CUDA events
+        are recorded around each stage: events[stage] = list of (start, end) pairs."""
+        L, plan, B = self.L, self.plan, self.B
+        s = self.stream
+        cs = s.cuda_stream
+        n_launch = 0
+
+        def timed(name, fn):
+            if events is None:
+                fn()
+                return
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            fn()
+            b.record(s)
+            events.setdefault(name, []).append((a, b))
+
+        with torch.cuda.device(self.dev), torch.cuda.stream(s):
+            if plan.any_progressive:
+                self.coef.zero_()
+            self.err.zero_()
+            timed("unstuff", lambda: _native.check(L.bj_unstuff(
+                self.raw.data_ptr(), self.scans.data_ptr(), len(plan.scans), self.tile_scan.data_ptr(), plan.n_tiles,
+                self.tile_sum.data_ptr(), self.words.data_ptr(), self.stream_start.data_ptr(),
+                self.stream_end.data_ptr(), plan.n_streams, cs), "bj_unstuff"))
+            n_launch += 3
+            timed("plan", lambda: _native.check(L.bj_entropy_plan(
+                self.scans.data_ptr(), 0, len(plan.scans), self.tile_sum.data_ptr(), ctypes.byref(B), cs),
+                "bj_entropy_plan"))
+            n_launch += 1
+            for gi, grp in enumerate(plan.groups):
+                if upto_group is not None and gi >= upto_group:
+                    break
+
+                def call(phases, grp=grp):
+                    _native.check(L.bj_entropy_decode(
+                        self.scans.data_ptr(), grp.first, grp.count, grp.mode, grp.max_sub, grp.max_streams,
+                        grp.max_blocks, grp.max_lut, ctypes.byref(B), self.chain.data_ptr(), phases, cs),
+                        "bj_entropy_decode")
+                if grp.mode in (0, 1, 3):
+                    if events is not None and grp.mode == 0:
+                        timed("spec", lambda: call(1))
+                        timed("fix", lambda: call(2))
+                        timed("write", lambda: call(4))
+                    else:
+                        timed("other_scans" if grp.mode else "entropy", lambda: call(7))
+                    n_launch += 3
+                else:
+                    timed("other_scans", lambda: call(7))
+                    n_launch += 1
+            if self.out is None or self._out_kind != out_kind:
+                self.out = None
+            holder = {}
+
+            def pix():
+                holder["out"] = run_pixels(self.dg, self.coef, _native.IN_COEF, out_kind, out=self.out, stream=s)
+            timed("pixels", pix)
+            self.out = holder["out"]
+            self._out_kind = out_kind
+            n_launch += 1
+        self.kernel_launches_per_step = n_launch
+        return self.out
+
+    def result(self) -> "DecodedBatch":
+        return DecodedBatch(self.plan, self.out, self.coef, self.err, {"sync_changes": self.sync_changes, "_pipe": self})
+
+
 def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed: Optional[Sequence[ParsedJpeg]] = None,
                            packed: Optional[Tuple[torch.Tensor, List[int]]] = None, check: bool = True,
                            stream: Optional[torch.cuda.Stream] = None, upto_wave: Optional[int] = None,
                            plan: Optional[BatchPlan] = None, out_kind: int = _native.OUT_RGB) -> DecodedBatch:
     """Decode a batch of JPEG file images on one GPU.  Returns device tensors; with check=True the
-    per-image error words are read back (one synchronisation) and turned into exceptions."""
-    dev = require_cuda(device)
-    L = _bind()
+    per-image error words are read back (one synchronisation) and turned into exceptions.
+    upto_wave=k stops the entropy stage after the first k scan groups (tests: per-scan parity)."""
+    require_cuda(device)
     if packed is None:
         packed = pack_files(datas)
     raw_host, offsets = packed
@@ -252,56 +375,10 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
         if parsed is None:
             parsed = [parse_jpeg(d) for d in datas]
         plan = BatchPlan(parsed, offsets, raw_host.numel())
-    g = plan.geom
-    with torch.cuda.device(dev):
-        s = stream if stream is not None else torch.cuda.current_stream(dev)
-        with torch.cuda.stream(s):
-            raw = raw_host.to(dev, non_blocking=True)
-            scans = to_device(plan.scans, dev, non_blocking=True)
-            tile_scan = to_device(plan.tile_scan, dev, non_blocking=True)
-            lut = torch.from_numpy(plan.lut.view(np.int32)).to(dev, non_blocking=True)
-            dg = DeviceGeometry(g, dev)
-            words_len = raw_host.numel() // 4 + 64
-            words = torch.empty(words_len, dtype=torch.int32, device=dev)
-            tile_sum = torch.empty(plan.n_tiles + 1, dtype=torch.int64, device=dev)
-            stream_start = torch.empty(plan.n_streams, dtype=torch.int64, device=dev)
-            stream_end = torch.empty(plan.n_streams, dtype=torch.int64, device=dev)
-            stream_sub = torch.empty(plan.n_streams, dtype=torch.int32, device=dev)
-            n_sub = max(plan.n_sub, 1)
-            sub_entry = torch.empty(n_sub, dtype=torch.int64, device=dev)
-            sub_exit = torch.empty(n_sub, dtype=torch.int64, device=dev)
-            sub_count = torch.empty(n_sub * 4, dtype=torch.int32, device=dev)
-            sub_prefix = torch.empty(n_sub * 4, dtype=torch.int32, device=dev)
-            chain = torch.empty(plan.max_chain * 8, dtype=torch.int32, device=dev)
-            if plan.any_progressive:
-                coef = torch.zeros((g.total_blocks, 64), dtype=torch.int16, device=dev)
-            else:
-                coef = torch.empty((g.total_blocks, 64), dtype=torch.int16, device=dev)
-            err = torch.zeros(len(plan.parsed), dtype=torch.int32, device=dev)
-            sync_changes = torch.zeros(1, dtype=torch.int32, device=dev)
-            B = EntropyBuffers(words.data_ptr(), words_len, stream_start.data_ptr(), stream_end.data_ptr(),
-                               stream_sub.data_ptr(), sub_entry.data_ptr(), sub_exit.data_ptr(),
-                               sub_count.data_ptr(), sub_prefix.data_ptr(), lut.data_ptr(), coef.data_ptr(),
-                               err.data_ptr(), sync_changes.data_ptr())
-            cs = s.cuda_stream
-            _native.check(L.bj_unstuff(raw.data_ptr(), scans.data_ptr(), len(plan.scans), tile_scan.data_ptr(),
-                                       plan.n_tiles, tile_sum.data_ptr(), words.data_ptr(), stream_start.data_ptr(),
-                                       stream_end.data_ptr(), plan.n_streams, cs), "bj_unstuff")
-            _native.check(L.bj_entropy_plan(scans.data_ptr(), 0, len(plan.scans), tile_sum.data_ptr(),
-                                            ctypes.byref(B), cs), "bj_entropy_plan")
-            for gi, grp in enumerate(plan.groups):
-                if upto_wave is not None and gi >= upto_wave:
-                    break
-                _native.check(L.bj_entropy_decode(scans.data_ptr(), grp.first, grp.count, grp.mode, grp.max_sub,
-                                                  grp.max_streams, grp.max_blocks, grp.max_lut, ctypes.byref(B),
-                                                  chain.data_ptr(), cs), "bj_entropy_decode")
-            out = run_pixels(dg, coef, _native.IN_COEF, out_kind, stream=s)
-            # keep the temporaries alive until the stream has consumed them
-            keep = (raw, scans, tile_scan, lut, words, tile_sum, stream_start, stream_end, stream_sub, sub_entry,
-                    sub_exit, sub_count, sub_prefix, chain, dg)
-            for t in keep[:-1]:
-                t.record_stream(s)
-    res = DecodedBatch(plan, out, coef, err, {"sync_changes": sync_changes, "_keep": keep})
+    pipe = DevicePipeline(plan, device, stream)
+    pipe.upload(raw_host)
+    pipe.launch(out_kind=out_kind, upto_group=upto_wave)
+    res = pipe.result()
     if check:
-        raise_for_errors(err.cpu().numpy())
+        raise_for_errors(pipe.err.cpu().numpy())
     return res
