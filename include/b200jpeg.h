@@ -77,7 +77,7 @@ typedef struct bj_image {
     uint8_t slot0[BJ_MAX_COMP];   /* first block slot of each component inside an MCU */
     uint16_t strip_mcus;          /* MCUs handled by one CTA of the pixel kernels (host-chosen, <= 192 / blocks_per_mcu) */
     uint16_t strips_per_row;      /* ceil(mcus_x / strip_mcus) */
-    uint32_t reserved;
+    uint32_t layout;              /* BJ_LAYOUT_*: selects the specialised pixel kernel (0 = generic) */
 } bj_image;
 
 /* ---------------------------------------------------------------------------------------------
@@ -200,6 +200,14 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
                             uint32_t max_streams, uint32_t max_blocks, uint32_t max_lut,
                             const bj_entropy_buffers* bufs, uint32_t* chain, int phases, void* stream);
 
+/* Sampling layouts with a specialised pixel kernel (chroma 1x1, luma HxV) */
+#define BJ_LAYOUT_GENERIC 0
+#define BJ_LAYOUT_420 1  /* luma 2x2 */
+#define BJ_LAYOUT_422 2  /* luma 2x1 */
+#define BJ_LAYOUT_440 3  /* luma 1x2 */
+#define BJ_LAYOUT_444 4  /* luma 1x1 */
+#define BJ_LAYOUT_GRAY 5 /* one component */
+
 /* Output selector of bj_pixels(). */
 #define BJ_OUT_RGB 0     /* uint8: fused IDCT + upsample + YCbCr->RGB (+ clamp)            */
 #define BJ_OUT_SAMPLES 1 /* int16 sample buffer: de-zigzag, dequantise, IDCT, +128 only    */
@@ -231,11 +239,15 @@ const char* bj_last_cuda_error(void);
  *               BJ_OUT_SAMPLES: int16 sample buffer (block indexing as the coefficient buffer);
  *               BJ_OUT_CANVAS: int16 (H, W, ncomp) per image at out_offset/out_pitch (int16 elements)
  *   max_strips  max over images of mcus_y * strips_per_row (grid x size)
+ *   layout_mask bit L set: some image has layout L.  For BJ_IN_COEF -> BJ_OUT_RGB the images with a
+ *               specialised layout (bits 1..5) run in the layout-specialised kernels and the generic
+ *               kernel only handles layout 0; layout_mask == 0 sends every image through the generic
+ *               kernel (the other in/out kinds always do).
  *   stats       optional device uint32[4]: [0] blocks recomputed exactly, [1] pixels recomputed exactly
  */
 bj_status bj_pixels(const bj_image* images, int n_images, int max_strips, const void* in, int in_kind,
                     const int16_t* qtabs, const double* idct_table_t, void* out, int out_kind,
-                    uint32_t* stats, void* stream);
+                    uint32_t layout_mask, uint32_t* stats, void* stream);
 
 #ifdef __cplusplus
 }

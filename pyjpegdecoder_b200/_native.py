@@ -21,13 +21,14 @@ IMAGE_DTYPE = np.dtype([
     ("qtab", "<u4", (3,)),
     ("ncomp", "u1"), ("hs", "u1", (3,)), ("vs", "u1", (3,)), ("hmax", "u1"), ("vmax", "u1"),
     ("blocks_per_mcu", "u1"), ("slot0", "u1", (3,)), ("pad0", "u1"),
-    ("strip_mcus", "<u2"), ("strips_per_row", "<u2"), ("pad1", "<u2"), ("reserved", "<u4"),
+    ("strip_mcus", "<u2"), ("strips_per_row", "<u2"), ("pad1", "<u2"), ("layout", "<u4"),
 ])
 assert IMAGE_DTYPE.itemsize == 72
 
 OUT_RGB, OUT_SAMPLES, OUT_CANVAS = 0, 1, 2
 IN_COEF, IN_SAMPLES = 0, 1
 PIXEL_MAX_BLOCKS = 192
+LAYOUT_GENERIC, LAYOUT_420, LAYOUT_422, LAYOUT_440, LAYOUT_444, LAYOUT_GRAY = range(6)
 
 ERR_BAD_CODE, ERR_OVERRUN, ERR_RST_COUNT, ERR_SYNC, ERR_COEF_INDEX = 1, 2, 4, 8, 16
 
@@ -51,7 +52,7 @@ def lib():
     L.bj_sizeof.argtypes = [c_int]
     L.bj_pixels.restype = c_int
     L.bj_pixels.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
-                            c_void_p, c_void_p]
+                            ctypes.c_uint32, c_void_p, c_void_p]
     if L.bj_sizeof(0) != IMAGE_DTYPE.itemsize:
         raise NativeLibraryError("struct bj_image layout mismatch between Python and libb200jpeg.so")
     _LIB = L

@@ -64,10 +64,15 @@ BJ_HD void idct8(float& x0, float& x1, float& x2, float& x3, float& x4, float& x
     x3 = a3 + o3; x4 = a3 - o3;
 }
 
-// fp32 error model of idct8x8_fast: |fast - exact| <= BJ_IDCT_ERR_REL * sum|coef| + BJ_IDCT_ERR_ABS.
-// Measured worst case over 2e8 random and structured blocks is 0.9e-7 * sum|coef|
-// (tests/hostsim); the constants keep a > 2x margin.
+// fp32 error model of idct8x8_fast:
+//   |fast - exact| <= BJ_IDCT_ERR_REL * sum|AC coef| + BJ_IDCT_ERR_DC * |DC| + BJ_IDCT_ERR_ABS.
+// Worst-case analysis of the 34-flop butterfly: at most 7 roundings of magnitude <= 0.5 * sum|x| per
+// 1-D pass (3.5 * 2^-24 per unit of sum|x|), two passes -> 2.1e-7 * sum|coef|; the DC term only
+// passes through 3 roundings per pass at gain 0.354 -> 7 * 2^-24 * 0.125 |DC| = 5.2e-8 |DC|.
+// Measured worst case over 1.1e9 samples of random/sparse/DC-heavy blocks: 5.3e-8 * sum|coef|
+// (tests/hostsim, tools/errprobe).
 #define BJ_IDCT_ERR_REL 2.4e-7f
+#define BJ_IDCT_ERR_DC 5.5e-8f
 #define BJ_IDCT_ERR_ABS 1.0e-6f
 
 // 2-D IDCT of one block held as f[v*8+u] (natural order); result f[y*8+x].
@@ -122,6 +127,19 @@ BJ_HD float div15_round(float n) {
     float w = fmaf(n, 1.0f / 15.0f, BJ_MAGIC);
     return w - BJ_MAGIC;
 }
+
+// ---- colour, integer-aware form (used by the layout-specialised kernel) ---------------------------
+// Y, Cb, Cr are integers (:1573, :1626), so R - Y = 1.402 (Cr-128), B - Y = 1.772 (Cb-128) and
+// G - Y = -0.34414 (Cb-128) - 0.71414 (Cr-128) take values on the grids k/500, k/250 and k/50000:
+//   * R - Y is a rounding tie only for Cr-128 = 250 (mod 500), otherwise at least 0.002 away;
+//   * B - Y is a tie only for Cb-128 = 125 (mod 250), otherwise at least 0.004 away;
+//   * G - Y can come within 2e-5 of a tie, or hit it exactly.
+// With |Cb-128|, |Cr-128| < 250 the fp32 offsets are within 4e-5 (R, B) and 3e-5 (G) of the exact
+// values, so R and B round correctly unless |Cb-128| == 125, and G is safe when it is farther than
+// BJ_G_ERR from a tie.  Everything else goes to the fp64 evaluation.  clip-then-round (:1698-1700)
+// equals clamp(Y + round(offset), 0, 255) away from ties.
+#define BJ_CHROMA_GUARD 250.0f
+#define BJ_G_ERR 3.0e-5f
 
 // ---- colour (YCbCr_to_RGB, :1683-1700) ---------------------------------------------------------
 // fp32 fast path.  err bound: each channel is at most two fused multiply-adds of magnitudes below

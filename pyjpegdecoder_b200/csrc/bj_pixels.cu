@@ -229,7 +229,7 @@ __device__ __forceinline__ void pixel_run(Smem& sm, const bj_image& im, int out_
 __global__ void __launch_bounds__(kThreads, 3)
 bj_pixels_kernel(const bj_image* __restrict__ images, const void* __restrict__ in, int in_kind,
                  const int16_t* __restrict__ qtabs, const double* __restrict__ tabT, void* __restrict__ out,
-                 int out_kind, uint32_t* __restrict__ stats) {
+                 int out_kind, int only_generic_layout, uint32_t* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     __shared__ bj_image im;
@@ -240,6 +240,7 @@ bj_pixels_kernel(const bj_image* __restrict__ images, const void* __restrict__ i
         if (tid < (int)(sizeof(bj_image) / 4)) reinterpret_cast<uint32_t*>(&im)[tid] = src[tid];
     }
     __syncthreads();
+    if (only_generic_layout && im.layout != BJ_LAYOUT_GENERIC) return;  // handled by bj_pixels_fast.cu
     const int strips_total = im.mcus_y * im.strips_per_row;
     if ((int)blockIdx.x >= strips_total) return;
     const int my = blockIdx.x / im.strips_per_row;
@@ -443,19 +444,33 @@ bj_status bj_set_cuda_error(cudaError_t e, const char* where) {
     return BJ_E_CUDA;
 }
 
+bj_status bj_pixels_fast_launch(const bj_image* images, int n_images, int max_strips, const int16_t* coef,
+                                const int16_t* qtabs, const double* tabT, uint8_t* out, uint32_t layout_mask,
+                                uint32_t* stats, void* stream);
+
 bj_status bj_pixels(const bj_image* images, int n_images, int max_strips, const void* in, int in_kind,
                     const int16_t* qtabs, const double* idct_table_t, void* out, int out_kind,
-                    uint32_t* stats, void* stream) {
+                    uint32_t layout_mask, uint32_t* stats, void* stream) {
     if (!images || n_images <= 0 || max_strips <= 0 || !in || !qtabs || !idct_table_t || !out) return BJ_E_ARG;
     if (n_images > 65535) return BJ_E_ARG;
     if (in_kind != BJ_IN_COEF && in_kind != BJ_IN_SAMPLES) return BJ_E_ARG;
     if (out_kind < BJ_OUT_RGB || out_kind > BJ_OUT_CANVAS) return BJ_E_ARG;
     static_assert(sizeof(bj_image) == 72, "bj_image layout");
+    int only_generic = 0;
+    if (in_kind == BJ_IN_COEF && out_kind == BJ_OUT_RGB && layout_mask != 0) {
+        if (layout_mask & ~1u) {
+            bj_status st = bj_pixels_fast_launch(images, n_images, max_strips, (const int16_t*)in, qtabs, idct_table_t,
+                                                 (uint8_t*)out, layout_mask, stats, stream);
+            if (st != BJ_OK) return st;
+        }
+        if (!(layout_mask & 1u)) return BJ_OK;
+        only_generic = 1;
+    }
     cudaError_t e = cudaFuncSetAttribute(bj_pixels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_pixels/attr");
     dim3 grid((unsigned)max_strips, (unsigned)n_images);
     bj_pixels_kernel<<<grid, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(images, in, in_kind, qtabs, idct_table_t, out,
-                                                                           out_kind, stats);
+                                                                           out_kind, only_generic, stats);
     e = cudaGetLastError();
     if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_pixels/launch");
     return BJ_OK;

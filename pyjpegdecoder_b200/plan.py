@@ -31,6 +31,17 @@ def idct_table_t() -> np.ndarray:
     return _IDCT_TABLE_T
 
 
+def layout_of(p: ParsedJpeg) -> int:
+    """BJ_LAYOUT_* code: which specialised pixel kernel handles the image (0 = generic)."""
+    if p.ncomp == 1:
+        return _native.LAYOUT_GRAY
+    c0, c1, c2 = p.components
+    if (c1.h, c1.v, c2.h, c2.v) != (1, 1, 1, 1):
+        return _native.LAYOUT_GENERIC
+    return {(2, 2): _native.LAYOUT_420, (2, 1): _native.LAYOUT_422, (1, 2): _native.LAYOUT_440,
+            (1, 1): _native.LAYOUT_444}.get((c0.h, c0.v), _native.LAYOUT_GENERIC)
+
+
 def choose_strip(mcus_x: int, blocks_per_mcu: int) -> int:
     """MCUs per CTA of the pixel kernel: as equal as possible, at most 192 blocks."""
     max_m = max(1, _native.PIXEL_MAX_BLOCKS // blocks_per_mcu)
@@ -53,6 +64,7 @@ class BatchGeometry:
         self.out_shapes = []
         self.block_offsets = []
         max_strips = 0
+        self.layout_mask = 0
         for i, p in enumerate(parsed):
             rec = self.images[i]
             ch = 3 if p.ncomp == 3 else 1
@@ -81,6 +93,8 @@ class BatchGeometry:
             strip = choose_strip(p.mcus_x, p.blocks_per_mcu)
             rec["strip_mcus"] = strip
             rec["strips_per_row"] = -(-p.mcus_x // strip)
+            rec["layout"] = layout_of(p)
+            self.layout_mask |= 1 << int(rec["layout"])
             max_strips = max(max_strips, int(rec["strips_per_row"]) * p.mcus_y)
             self.block_offsets.append(blk)
             self.out_offsets.append(out)

@@ -49,7 +49,7 @@ class DeviceGeometry:
 
 def run_pixels(dg: DeviceGeometry, inp: torch.Tensor, in_kind: int, out_kind: int,
                out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-               stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+               stream: Optional[torch.cuda.Stream] = None, force_generic: bool = False) -> torch.Tensor:
     """bj_pixels(): coefficient (or sample) buffer -> RGB / samples / canvas."""
     g = dg.geom
     L = _native.lib()
@@ -64,6 +64,7 @@ def run_pixels(dg: DeviceGeometry, inp: torch.Tensor, in_kind: int, out_kind: in
     with torch.cuda.device(dg.device):
         st = L.bj_pixels(dg.images.data_ptr(), len(g.parsed), g.max_strips, inp.data_ptr(), in_kind,
                          dg.qtabs.data_ptr(), dg.table.data_ptr(), out.data_ptr(), out_kind,
+                         0 if force_generic else g.layout_mask,
                          stats.data_ptr() if stats is not None else None, s.cuda_stream)
     _native.check(st, "bj_pixels")
     return out

@@ -3,6 +3,7 @@
 // (the header is __host__ __device__ and uses explicit fmaf only).  Never used by the product.
 #include <cstdint>
 #include <cmath>
+#include <cstring>
 #include "../../pyjpegdecoder_b200/csrc/bj_pixel_math.cuh"
 
 extern "C" {
@@ -15,10 +16,10 @@ void hs_idct_blocks(const int32_t* blocks, int n, int16_t* out, uint8_t* flagged
         float S = 0.f;
         for (int k = 0; k < 64; k++) {
             f[k] = (float)blocks[b * 64 + k];
-            S += fabsf(f[k]);
+            if (k) S += fabsf(f[k]);
         }
+        const float T = fmaf(S, BJ_IDCT_ERR_REL, fmaf(fabsf(f[0]), BJ_IDCT_ERR_DC, BJ_IDCT_ERR_ABS));
         bj::idct8x8_fast(f);
-        const float T = fmaf(S, BJ_IDCT_ERR_REL, BJ_IDCT_ERR_ABS);
         float mind = 1.0f;
         for (int k = 0; k < 64; k++) {
             float td;
@@ -48,6 +49,23 @@ void hs_weights(int rh, int rv, int32_t* w, int32_t* cell) {
 }
 
 float hs_div15(float n) { return bj::div15_round(n); }
+
+// integer-aware colour path of the specialised kernel: returns rgb and the "needs fp64" flag per pixel
+void hs_color2(const int16_t* ycc, int n, uint8_t* rgb, uint8_t* slow) {
+    for (int i = 0; i < n; i++) {
+        int Y = ycc[3 * i];
+        float cbm = (float)ycc[3 * i + 1] - 128.0f, crm = (float)ycc[3 * i + 2] - 128.0f;
+        float rC = 1.402f * crm, gC = fmaf(-0.71414f, crm, -0.34414f * cbm), bC = 1.772f * cbm;
+        float wr = rC + BJ_MAGIC, wg = gC + BJ_MAGIC, wb = bC + BJ_MAGIC;
+        float dg = fabsf(gC - (wg - BJ_MAGIC));
+        bool s = fmaxf(fabsf(cbm), fabsf(crm)) >= BJ_CHROMA_GUARD || fabsf(cbm) == 125.0f || dg > 0.5f - BJ_G_ERR;
+        int32_t ir, ig, ib;
+        memcpy(&ir, &wr, 4); memcpy(&ig, &wg, 4); memcpy(&ib, &wb, 4);
+        int v[3] = {Y + ir - BJ_MAGIC_BITS, Y + ig - BJ_MAGIC_BITS, Y + ib - BJ_MAGIC_BITS};
+        for (int c = 0; c < 3; c++) rgb[3 * i + c] = (uint8_t)(v[c] < 0 ? 0 : (v[c] > 255 ? 255 : v[c]));
+        slow[i] = s;
+    }
+}
 
 // colour fast path for n pixels; tie[i] = 1 when the kernel would take the fp64 path
 void hs_color(const int16_t* ycc, int n, uint8_t* rgb, uint8_t* tie) {

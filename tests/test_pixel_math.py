@@ -123,6 +123,27 @@ def test_div15_round_exact(hs):
     assert np.array_equal(got, want[::7])
 
 
+def test_colour_integer_aware_path_never_accepts_a_wrong_pixel(hs):
+    """The specialised kernel's colour path: exhaustive over Cb, Cr in [-130, 390] and a few Y."""
+    cb, cr = np.meshgrid(np.arange(-130, 391), np.arange(-130, 391), indexing="ij")
+    for Y in (-7, 0, 1, 100, 128, 255, 301):
+        ycc = np.stack([np.full(cb.size, Y), cb.ravel(), cr.ravel()], -1).astype(np.int16)
+        n = ycc.shape[0]
+        rgb = np.empty((n, 3), np.uint8)
+        slow = np.empty(n, np.uint8)
+        hs.hs_color2(ycc.ctypes.data_as(ctypes.c_void_p), n, rgb.ctypes.data_as(ctypes.c_void_p),
+                     slow.ctypes.data_as(ctypes.c_void_p))
+        Yf, Cb, Cr = (ycc[:, k].astype(np.float64) for k in range(3))
+        R = Yf + 1.402 * (Cr - 128.0)
+        G = Yf - 0.34414 * (Cb - 128.0) - 0.71414 * (Cr - 128.0)
+        B = Yf + 1.772 * (Cb - 128.0)
+        want = np.round(np.clip(np.stack((R, G, B), -1), 0.0, 255.0)).astype(np.uint8)
+        ok = slow == 0
+        assert np.array_equal(rgb[ok], want[ok]), Y
+        inside = (np.abs(Cb - 128) < 128) & (np.abs(Cr - 128) < 128)
+        assert slow[inside].mean() < 0.02
+
+
 def test_colour_fast_path_never_accepts_a_wrong_pixel(hs):
     rng = np.random.default_rng(5)
     n = 400000

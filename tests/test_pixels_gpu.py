@@ -36,7 +36,10 @@ def test_pixels_all_golden_cases_one_batch():
     canvas = stages.run_pixels(dg, coef_t, nat.IN_COEF, nat.OUT_CANVAS)
     samples = stages.run_pixels(dg, coef_t, nat.IN_COEF, nat.OUT_SAMPLES)
     rgb2 = stages.run_pixels(dg, samples, nat.IN_SAMPLES, nat.OUT_RGB)
+    rgb3 = stages.run_pixels(dg, coef_t, nat.IN_COEF, nat.OUT_RGB, force_generic=True)   # generic kernel only
     torch.cuda.synchronize()
+    for a, b in zip(stages.image_views(geom, rgb), stages.image_views(geom, rgb3)):
+        assert torch.equal(a, b), "layout-specialised and generic pixel kernels disagree"
     rgb_v = stages.image_views(geom, rgb)
     rgb2_v = stages.image_views(geom, rgb2)
     can_v = stages.image_views(geom, canvas)
