@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ sca
                                                  uint32_t lut_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
-    load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
-    const uint32_t base = blockIdx.x * T;
+    load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
+    const uint32_t base = blockIdx.y * T;
     if (base >= sh.scan_nsub) return;
     const uint32_t lscan = base + threadIdx.x;
     SubInfo si = locate(sh, B, lscan);
@@ -260,20 +260,27 @@ __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ sca
 }
 
 // ---- chained fix-up + prefix sums --------------------------------------------------------------------
+// Re-decodes are COMPACTED: in every round the subsequences whose entry state changed are collected
+// into a dense list and decoded by the first threads of the CTA, so that warps stay full even when
+// only a few subsequences per round need work.
 __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
                                                 uint32_t* __restrict__ chain, uint32_t lut_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
-    __shared__ uint64_t s_exit[T];
+    __shared__ uint64_t s_entry[T], s_exit[T];
+    __shared__ uint64_t s_own[T], s_stop[T], s_b1[T];
     __shared__ uint32_t s_cnt[T][4];
     __shared__ uint32_t s_head[T];
+    __shared__ uint16_t s_list[T];
+    __shared__ uint32_t s_wcount[T / 32];
+    __shared__ uint32_t s_tail[T / 32][4];
     __shared__ uint64_t s_prev_exit;
     __shared__ uint32_t s_carry[4];
     __shared__ uint64_t first_bit;
-    load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
-    const uint32_t base = blockIdx.x * T;
+    load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
+    const uint32_t base = blockIdx.y * T;
     if (base >= sh.scan_nsub) return;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lscan = base + tid;
     SubInfo si = locate(sh, B, lscan);
     if (tid == 0) first_bit = si.own;
@@ -281,41 +288,70 @@ __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scan
     load_window(sh, B, first_bit);
     WinSrc src = win_src(sh, B);
     const size_t g = (size_t)sh.sc.sub0 + lscan;
-    uint64_t entry = 0, ex = 0;
-    SubCount k{0, {0, 0, 0}};
-    if (si.valid) {
-        entry = B.sub_entry[g];
-        ex = B.sub_exit[g];
-        uint4 c = reinterpret_cast<const uint4*>(B.sub_count)[g];
-        k.blocks = c.x; k.dc[0] = (int)c.y; k.dc[1] = (int)c.z; k.dc[2] = (int)c.w;
+    {
+        uint64_t entry = 0, ex = 0;
+        uint4 c = make_uint4(0, 0, 0, 0);
+        if (si.valid) {
+            entry = B.sub_entry[g];
+            ex = B.sub_exit[g];
+            c = reinterpret_cast<const uint4*>(B.sub_count)[g];
+        }
+        s_entry[tid] = entry;
+        s_exit[tid] = ex;
+        s_cnt[tid][0] = c.x; s_cnt[tid][1] = c.y; s_cnt[tid][2] = c.z; s_cnt[tid][3] = c.w;
+        s_own[tid] = si.own; s_stop[tid] = si.stop; s_b1[tid] = si.b1;
     }
     const bool head = si.valid && si.l == 0;          // entry state known exactly
     const bool needs_prev_cta = (tid == 0) && si.valid && !head;
+    // CTAs of one scan are gridDim.x apart in launch order: by the time chunk c of a scan starts, chunk
+    // c-1 (launched a whole grid row earlier) is usually finished, so the chain wait rarely spins.
     uint32_t* my_chain = chain + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kChainWords;
-    const uint32_t* prev_chain = my_chain - kChainWords;
+    const uint32_t* prev_chain = my_chain - (size_t)gridDim.x * kChainWords;
     uint32_t changes = 0;
+    if (tid == 0) s_prev_exit = s_entry[0];
+    __syncthreads();
 
     auto converge = [&]() {
         for (;;) {
-            s_exit[tid] = ex;
-            __syncthreads();
-            int mine = 0;
+            // who needs a new entry state?
+            bool need = false;
+            uint64_t want = 0;
             if (si.valid && !head) {
-                uint64_t want = (tid == 0) ? s_prev_exit : s_exit[tid - 1];
-                if (entry != want) {
-                    entry = want;
-                    run_sub(sh, src, si, entry, ex, k);
-                    mine = 1;
-                    changes++;
-                }
+                want = (tid == 0) ? s_prev_exit : s_exit[tid - 1];
+                need = s_entry[tid] != want;
             }
-            if (!__syncthreads_or(mine)) break;
+            const unsigned bal = __ballot_sync(0xffffffffu, need);
+            if (lane == 0) s_wcount[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t off = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < T / 32; w++) {
+                uint32_t cw = s_wcount[w];
+                if (w < warp) off += cw;
+                total += cw;
+            }
+            if (total == 0) break;
+            if (need) {
+                s_entry[tid] = want;
+                s_list[off + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)tid;
+            }
+            __syncthreads();
+            if ((uint32_t)tid < total) {  // dense: item i is decoded by thread i
+                const int j = s_list[tid];
+                SubInfo sj;
+                sj.own = s_own[j]; sj.stop = s_stop[j]; sj.b1 = s_b1[j];
+                uint64_t ex;
+                SubCount k;
+                run_sub(sh, src, sj, s_entry[j], ex, k);
+                s_exit[j] = ex;
+                s_cnt[j][0] = k.blocks; s_cnt[j][1] = (uint32_t)k.dc[0]; s_cnt[j][2] = (uint32_t)k.dc[1]; s_cnt[j][3] = (uint32_t)k.dc[2];
+                changes++;
+            }
+            __syncthreads();
         }
     };
 
     // 1. local convergence with the speculative entry of the CTA's first subsequence
-    if (tid == 0) s_prev_exit = entry;
-    __syncthreads();
     converge();
     // 2. chain: wait for the previous CTA of this scan, repair if its final exit state differs
     if (tid == 0) {
@@ -326,22 +362,56 @@ __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scan
             __threadfence();
             s_prev_exit = (uint64_t)pc[0] | ((uint64_t)pc[1] << 32);
             carry[0] = pc[2]; carry[1] = pc[3]; carry[2] = pc[4]; carry[3] = pc[5];
-        } else {
-            s_prev_exit = entry;
         }
         for (int i = 0; i < 4; i++) s_carry[i] = carry[i];
     }
     __syncthreads();
     converge();
-    // 3. segmented exclusive prefix over the CTA (segments start at stream heads)
-    s_head[tid] = head ? 1u : 0u;
-    s_cnt[tid][0] = si.valid ? k.blocks : 0u;
-    s_cnt[tid][1] = si.valid ? (uint32_t)k.dc[0] : 0u;
-    s_cnt[tid][2] = si.valid ? (uint32_t)k.dc[1] : 0u;
-    s_cnt[tid][3] = si.valid ? (uint32_t)k.dc[2] : 0u;
-    if (tid == 0 && !head) {  // carry-in from the previous CTA belongs to thread 0's segment
-        for (int i = 0; i < 4; i++) s_cnt[0][i] += s_carry[i];
+    // 3. publish early: exit state of the CTA's last subsequence and the running totals of the stream
+    //    that is open at the CTA's end = counts since the last stream head (+ carry-in if none).
+    const uint32_t last = min((uint32_t)T, sh.scan_nsub - base) - 1;
+    uint32_t own[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) own[i] = si.valid ? s_cnt[tid][i] : 0u;
+    {
+        const unsigned hb = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_wcount[warp] = hb;
+        __syncthreads();
+        // index of the last head in the CTA (or -1)
+        int last_head = -1;
+#pragma unroll
+        for (int w = 0; w < T / 32; w++)
+            if (s_wcount[w]) last_head = w * 32 + 31 - __clz(s_wcount[w]);
+        const bool in_tail = si.valid && tid >= last_head;  // last_head = -1: every valid thread
+        uint32_t v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            v[i] = in_tail ? own[i] : 0u;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        }
+        __syncthreads();
+        if (lane == 0) { s_tail[warp][0] = v[0]; s_tail[warp][1] = v[1]; s_tail[warp][2] = v[2]; s_tail[warp][3] = v[3]; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t tot[4];
+            for (int i = 0; i < 4; i++) {
+                tot[i] = (last_head < 0) ? s_carry[i] : 0u;
+                for (int w = 0; w < T / 32; w++) tot[i] += s_tail[w][i];
+            }
+            const uint64_t ex = s_exit[last];
+            my_chain[0] = (uint32_t)ex;
+            my_chain[1] = (uint32_t)(ex >> 32);
+            my_chain[2] = tot[0]; my_chain[3] = tot[1]; my_chain[4] = tot[2]; my_chain[5] = tot[3];
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(my_chain + 6) = 1u;
+        }
     }
+    // 4. segmented exclusive prefix over the CTA (segments start at stream heads)
+    __syncthreads();
+    s_head[tid] = head ? 1u : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) s_cnt[tid][i] = own[i] + ((tid == 0 && !head) ? s_carry[i] : 0u);
     __syncthreads();
     for (int o = 1; o < T; o <<= 1) {  // inclusive segmented scan (Hillis-Steele)
         uint32_t a[4] = {0, 0, 0, 0};
@@ -359,24 +429,11 @@ __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scan
         __syncthreads();
     }
     if (si.valid) {
-        uint32_t own[4] = {k.blocks, (uint32_t)k.dc[0], (uint32_t)k.dc[1], (uint32_t)k.dc[2]};
         uint4 pre = make_uint4(s_cnt[tid][0] - own[0], s_cnt[tid][1] - own[1], s_cnt[tid][2] - own[2], s_cnt[tid][3] - own[3]);
-        B.sub_entry[g] = entry;
-        B.sub_exit[g] = ex;
+        B.sub_entry[g] = s_entry[tid];
+        B.sub_exit[g] = s_exit[tid];
         reinterpret_cast<uint4*>(B.sub_count)[g] = make_uint4(own[0], own[1], own[2], own[3]);
         reinterpret_cast<uint4*>(B.sub_prefix)[g] = pre;
-    }
-    // 4. publish: exit state and running totals (of the stream that is open at the CTA's end)
-    uint32_t last = min((uint32_t)T, sh.scan_nsub - base) - 1;
-    if (tid == (int)last) {
-        my_chain[0] = (uint32_t)ex;
-        my_chain[1] = (uint32_t)(ex >> 32);
-        my_chain[2] = s_cnt[tid][0];
-        my_chain[3] = s_cnt[tid][1];
-        my_chain[4] = s_cnt[tid][2];
-        my_chain[5] = s_cnt[tid][3];
-        __threadfence();
-        *reinterpret_cast<volatile uint32_t*>(my_chain + 6) = 1u;
     }
     if (changes && B.sync_changes) atomicAdd(B.sync_changes, changes);
 }
@@ -390,20 +447,15 @@ __device__ __forceinline__ size_t block_address(const bj_scan& sc, uint32_t mcu,
 }
 
 // Baseline block sink: the thread's block lives in shared memory as 8 chunks of 16 bytes, chunk c of
-// thread t at (c * T + t) * 16 (conflict-free 128-bit access across lanes); the four 32-bit words of a
-// chunk are XOR-permuted by (t >> 3) & 3 so that 16-bit stores of neighbouring lanes spread over banks.
+// thread t at (c * T + t) * 16: conflict-free 128-bit reads when the block is flushed.
 struct SmemBlockSink {
-    uint32_t* buf;  // T * 32 words
-    int tid;
-    int perm;
+    unsigned char* base;  // buf + tid * 16
     int16_t* coef;
     const bj_scan* sc;
     uint32_t mcu0;
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void put(int z, int16_t v) {
-        int chunk = z >> 3, w = ((z & 7) >> 1) ^ perm;
-        int16_t* p = reinterpret_cast<int16_t*>(buf + (chunk * T + tid) * 4 + w) + (z & 1);
-        *p = v;
+        *reinterpret_cast<int16_t*>(base + (z >> 3) * (T * 16) + ((z & 7) << 1)) = v;
     }
     __device__ __forceinline__ void commit(uint32_t blk, int slot) {
         uint32_t mcu = mcu0 + blk / sc->nslots;
@@ -411,11 +463,9 @@ struct SmemBlockSink {
         const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            uint4* s = reinterpret_cast<uint4*>(buf + (c * T + tid) * 4);
+            uint4* s = reinterpret_cast<uint4*>(base + c * (T * 16));
             uint4 v = *s;
             *s = zero;
-            if (perm & 1) { uint32_t t0 = v.x; v.x = v.y; v.y = t0; t0 = v.z; v.z = v.w; v.w = t0; }
-            if (perm & 2) { uint32_t t0 = v.x; v.x = v.z; v.z = t0; t0 = v.y; v.y = v.w; v.w = t0; }
             dst[c] = v;
         }
     }
@@ -440,8 +490,8 @@ __global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ sc
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
     __shared__ __align__(16) uint32_t s_blocks[T * 32];
     __shared__ uint64_t first_bit;
-    load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
-    const uint32_t base = blockIdx.x * T;
+    load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
+    const uint32_t base = blockIdx.y * T;
     if (base >= sh.scan_nsub) return;
     const int tid = threadIdx.x;
     const uint32_t lscan = base + tid;
@@ -463,7 +513,7 @@ __global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ sc
     uint32_t err = 0;
     const int mode = sh.sc.mode;
     if (mode == BJ_MODE_BASELINE) {
-        SmemBlockSink sink{s_blocks, tid, (tid >> 3) & 3, B.coef, &sh.sc, si.mcu0};
+        SmemBlockSink sink{reinterpret_cast<unsigned char*>(s_blocks) + tid * 16, B.coef, &sh.sc, si.mcu0};
         err = base_write_run(rd, z, slot, sh.ctx, si.stop, si.b1, blk, si.nblk_stream, pred, sink);
     } else if (mode == BJ_MODE_DC_FIRST) {
         GlobalCoefSink sink{B.coef, &sh.sc, si.mcu0};
@@ -562,7 +612,8 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
-        dim3 grid((max_sub + T - 1) / T, (unsigned)n_scans);
+        dim3 grid((unsigned)n_scans, (max_sub + T - 1) / T);
+        if (grid.y > 65535) return BJ_E_ARG;
         if (phases & BJ_PHASE_SPEC) spec_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
         if (phases & BJ_PHASE_FIX) {
             e = cudaMemsetAsync(chain, 0, sizeof(uint32_t) * kChainWords * (size_t)grid.x * grid.y, st);

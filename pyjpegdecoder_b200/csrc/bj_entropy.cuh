@@ -57,41 +57,51 @@ BJ_HD int ent_adv(uint32_t e) { return (int)((e >> 18) & 127u); }
 BJ_HD int extend(uint32_t v, int n) { return (n == 0) ? 0 : ((v >> (n - 1)) ? (int)v : (int)v - ((1 << n) - 1)); }
 
 // ---- bit reader over big-endian 32-bit words -----------------------------------------------------
+// Two 32-bit words (w0 = current, w1 = next) and the number of bits of w0 already consumed: the next
+// 32 bits are one funnel shift away, consuming bits is an add, and a refill is one word fetch about
+// every third symbol.  One symbol never needs more than 16 code bits + 15 value bits = 31 bits.
+BJ_HD uint32_t funnel_left(uint32_t hi, uint32_t lo, int sh) {  // upper 32 bits of (hi:lo) << sh, 0 <= sh < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, sh);
+#else
+    return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+#endif
+}
+
 template <class Src>
 struct BitReader {
     const Src* src;
-    uint64_t buf;   // next bits, MSB first
-    int avail;      // valid bits in buf (> 32 between symbols)
-    uint32_t next;  // next word to fetch
-    uint64_t pos;   // absolute bit position of buf's MSB
+    uint32_t w0, w1;  // current and next word
+    int o;            // bits of w0 consumed (0..31)
+    uint32_t next;    // next word to fetch
+    uint64_t pos;     // absolute bit position
 
     BJ_HDM void seek(const Src* s, uint64_t p) {
         src = s;
         pos = p;
         uint32_t w = (uint32_t)(p >> 5);
-        int sh = (int)(p & 31);
-        uint64_t hi = src->word(w), lo = src->word(w + 1);
-        buf = ((hi << 32) | lo) << sh;
-        avail = 64 - sh;
+        o = (int)(p & 31);
+        w0 = src->word(w);
+        w1 = src->word(w + 1);
         next = w + 2;
-        if (avail <= 32) {
-            buf |= (uint64_t)src->word(next++) << (32 - avail);
-            avail += 32;
-        }
     }
-    BJ_HDM uint32_t peek16() const { return (uint32_t)(buf >> 48); }
-    // n bits (1..16) that follow the first `skipn` bits
-    BJ_HDM uint32_t bits_after(int skipn, int n) const { return (uint32_t)((buf << skipn) >> (64 - n)); }
+    BJ_HDM uint32_t peek32() const { return funnel_left(w0, w1, o); }
+    BJ_HDM uint32_t peek16() const { return peek32() >> 16; }
+    // n bits (1..16) that follow the first `skipn` bits (skipn + n <= 32)
+    BJ_HDM uint32_t bits_after(int skipn, int n) const { return (peek32() << skipn) >> (32 - n); }
     BJ_HDM void skip(int n) {  // n <= 32
-        buf <<= n;
-        avail -= n;
+        o += n;
         pos += (uint64_t)n;
-        if (avail <= 32) {
-            buf |= (uint64_t)src->word(next++) << (32 - avail);
-            avail += 32;
+        if (o >= 32) {
+            o -= 32;
+            w0 = w1;
+            w1 = src->word(next++);
         }
     }
 };
+
+// value bits of a symbol taken from an already fetched 32-bit look-ahead
+BJ_HD uint32_t take_bits(uint32_t pk, int skipn, int n) { return (pk << skipn) >> (32 - n); }
 
 // ---- per-scan context (shared memory on the device) ----------------------------------------------
 struct ScanCtx {
@@ -129,19 +139,21 @@ BJ_HD bool at_padding(const BitReader<Src>& rd, uint64_t stream_end) {
 template <int MODE, class Src>
 BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, uint64_t own_start, uint64_t stop,
                     uint64_t stream_end, SubCount& cnt) {
+    const uint32_t* const lut = c.lut;
+    const int nslots = c.nslots;
     while (rd.pos < stop) {
-        uint32_t pk = rd.peek16();
         if (z == 0) {
             if (stream_end - rd.pos < 8 && at_padding(rd, stream_end)) {
                 rd.pos = stream_end;
                 break;
             }
-            uint32_t e = lut_lookup(c.lut + c.dc_tab[slot], pk);
+            const uint32_t pk = rd.peek32();
+            uint32_t e = lut_lookup(lut + c.dc_tab[slot], pk >> 16);
             int L = ent_len(e), t = ent_sym(e), tot = ent_total(e);
             if (L == 0) { L = 1; t = 0; tot = 1; }  // not a code: any deterministic step will do while speculating
             if (rd.pos >= own_start) {
                 cnt.blocks++;
-                int diff = extend(t ? rd.bits_after(L, t) : 0u, t);
+                int diff = extend(t ? take_bits(pk, L, t) : 0u, t);
                 int k = c.slot_comp[slot];
                 if (k == 0) cnt.dc[0] += diff;
                 else if (k == 1) cnt.dc[1] += diff;
@@ -150,15 +162,18 @@ BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, uin
             rd.skip(tot);
             z = (MODE == BJ_M_DCFIRST) ? 64 : 1;
         } else {
-            uint32_t e = lut_lookup(c.lut + c.ac_tab[slot], pk);
-            int L = ent_len(e);
-            int tot = L ? ent_total(e) : 1, adv = L ? ent_adv(e) : 1;
-            rd.skip(tot);
-            z += adv;
+            const uint32_t* const tab = lut + c.ac_tab[slot];
+            do {
+                uint32_t e = lut_lookup(tab, rd.peek16());
+                int L = ent_len(e);
+                int tot = L ? ent_total(e) : 1, adv = L ? ent_adv(e) : 1;
+                rd.skip(tot);
+                z += adv;
+            } while (z < 64 && rd.pos < stop);
         }
         if (z >= 64) {
             z = 0;
-            slot = (slot + 1 == c.nslots) ? 0 : slot + 1;
+            slot = (slot + 1 == nslots) ? 0 : slot + 1;
         }
     }
 }
@@ -170,25 +185,28 @@ BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, uin
 template <class Src, class Sink>
 BJ_HD uint32_t base_write_run(BitReader<Src>& rd, int z, int slot, const ScanCtx& c, uint64_t stop, uint64_t stream_end,
                               uint32_t& blk, uint32_t nblk_stream, int pred[3], Sink& sink) {
+    const uint32_t* const lut = c.lut;
+    const int nslots = c.nslots;
     // finish (without writing) the block that the previous subsequence started
-    while (z != 0) {
-        if (rd.pos >= stream_end + 64) return BJ_ERR_OVERRUN;
-        uint32_t e = lut_lookup(c.lut + c.ac_tab[slot], rd.peek16());
-        if (ent_len(e) == 0) return BJ_ERR_BAD_CODE;
-        rd.skip(ent_total(e));
-        z += ent_adv(e);
-        if (z >= 64) {
-            z = 0;
-            slot = (slot + 1 == c.nslots) ? 0 : slot + 1;
+    if (z != 0) {
+        const uint32_t* const tab = lut + c.ac_tab[slot];
+        while (z < 64) {
+            if (rd.pos >= stream_end + 64) return BJ_ERR_OVERRUN;
+            uint32_t e = lut_lookup(tab, rd.peek16());
+            if (ent_len(e) == 0) return BJ_ERR_BAD_CODE;
+            rd.skip(ent_total(e));
+            z += ent_adv(e);
         }
+        slot = (slot + 1 == nslots) ? 0 : slot + 1;
     }
     while (rd.pos < stop && blk < nblk_stream) {
         sink.begin();
         {
-            uint32_t e = lut_lookup(c.lut + c.dc_tab[slot], rd.peek16());
+            const uint32_t pk = rd.peek32();
+            uint32_t e = lut_lookup(lut + c.dc_tab[slot], pk >> 16);
             int L = ent_len(e), t = ent_sym(e);
             if (L == 0) return BJ_ERR_BAD_CODE;
-            int diff = extend(t ? rd.bits_after(L, t) : 0u, t);
+            int diff = extend(t ? take_bits(pk, L, t) : 0u, t);
             int k = c.slot_comp[slot];
             int pv;
             if (k == 0) pv = (pred[0] += diff);
@@ -197,21 +215,23 @@ BJ_HD uint32_t base_write_run(BitReader<Src>& rd, int z, int slot, const ScanCtx
             sink.put(0, (int16_t)pv);  // previous_dc is int16 (:735, :818-820)
             rd.skip(ent_total(e));
         }
+        const uint32_t* const tab = lut + c.ac_tab[slot];
         int zz = 1;
         while (zz < 64) {
-            uint32_t e = lut_lookup(c.lut + c.ac_tab[slot], rd.peek16());
-            int L = ent_len(e), rs = ent_sym(e);
+            const uint32_t pk = rd.peek32();
+            uint32_t e = lut_lookup(tab, pk >> 16);
+            int L = ent_len(e), tot = ent_total(e);
             if (L == 0) return BJ_ERR_BAD_CODE;
-            int s = rs & 15;
+            int s = tot - L;
             zz += ent_adv(e) - 1;  // zero run (EOB: jumps past 63, ZRL: 15)
-            if (zz < 64 && s) sink.put(zz, (int16_t)extend(rd.bits_after(L, s), s));
-            rd.skip(ent_total(e));
+            if (s && zz < 64) sink.put(zz, (int16_t)extend(take_bits(pk, L, s), s));
+            rd.skip(tot);
             zz++;
         }
         if (rd.pos > stream_end + 7) return BJ_ERR_OVERRUN;
         sink.commit(blk, slot);
         blk++;
-        slot = (slot + 1 == c.nslots) ? 0 : slot + 1;
+        slot = (slot + 1 == nslots) ? 0 : slot + 1;
     }
     return 0;
 }
@@ -221,10 +241,11 @@ template <class Src, class Sink>
 BJ_HD uint32_t dcfirst_write_run(BitReader<Src>& rd, int slot, const ScanCtx& c, uint64_t stop, uint64_t stream_end,
                                  uint32_t& blk, uint32_t nblk_stream, int pred[3], Sink& sink) {
     while (rd.pos < stop && blk < nblk_stream) {
-        uint32_t e = lut_lookup(c.lut + c.dc_tab[slot], rd.peek16());
+        const uint32_t pk = rd.peek32();
+        uint32_t e = lut_lookup(c.lut + c.dc_tab[slot], pk >> 16);
         int L = ent_len(e), t = ent_sym(e);
         if (L == 0) return BJ_ERR_BAD_CODE;
-        int diff = extend(t ? rd.bits_after(L, t) : 0u, t);
+        int diff = extend(t ? take_bits(pk, L, t) : 0u, t);
         int k = c.slot_comp[slot];
         int pv;
         if (k == 0) pv = (pred[0] += diff);
