@@ -136,22 +136,29 @@ BJ_HD bool at_padding(const BitReader<Src>& rd, uint64_t stream_end) {
 // ---- baseline / DC-first: counting pass ----------------------------------------------------------
 // Decode from (rd.pos, z, slot) until rd.pos >= stop.  Blocks whose DC symbol starts at a position
 // >= own_start are counted and their DC differences summed.  Nothing is written.
+// The loops below are FLAT: every iteration decodes exactly one symbol (DC or AC, chosen by a table
+// select), so the 32 lanes of a warp stay converged even though their blocks have different numbers
+// of symbols; only the short DC / end-of-block bodies diverge.
 template <int MODE, class Src>
 BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, uint64_t own_start, uint64_t stop,
                     uint64_t stream_end, SubCount& cnt) {
     const uint32_t* const lut = c.lut;
     const int nslots = c.nslots;
+    uint32_t dct = c.dc_tab[slot], act = c.ac_tab[slot];
     while (rd.pos < stop) {
-        if (z == 0) {
-            if (stream_end - rd.pos < 8 && at_padding(rd, stream_end)) {
-                rd.pos = stream_end;
-                break;
-            }
-            const uint32_t pk = rd.peek32();
-            uint32_t e = lut_lookup(lut + c.dc_tab[slot], pk >> 16);
-            int L = ent_len(e), t = ent_sym(e), tot = ent_total(e);
-            if (L == 0) { L = 1; t = 0; tot = 1; }  // not a code: any deterministic step will do while speculating
+        const bool is_dc = (z == 0);
+        if (is_dc && stream_end - rd.pos < 8 && at_padding(rd, stream_end)) {
+            rd.pos = stream_end;
+            break;
+        }
+        const uint32_t pk = rd.peek32();
+        const uint32_t e = lut_lookup(lut + (is_dc ? dct : act), pk >> 16);
+        const int L = ent_len(e);
+        int tot = ent_total(e), adv = ent_adv(e);
+        if (L == 0) { tot = 1; adv = 1; }  // not a code: any deterministic step will do while speculating
+        if (is_dc) {
             if (rd.pos >= own_start) {
+                const int t = L ? ent_sym(e) : 0;
                 cnt.blocks++;
                 int diff = extend(t ? take_bits(pk, L, t) : 0u, t);
                 int k = c.slot_comp[slot];
@@ -159,35 +166,32 @@ BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, uin
                 else if (k == 1) cnt.dc[1] += diff;
                 else cnt.dc[2] += diff;
             }
-            rd.skip(tot);
-            z = (MODE == BJ_M_DCFIRST) ? 64 : 1;
-        } else {
-            const uint32_t* const tab = lut + c.ac_tab[slot];
-            do {
-                uint32_t e = lut_lookup(tab, rd.peek16());
-                int L = ent_len(e);
-                int tot = L ? ent_total(e) : 1, adv = L ? ent_adv(e) : 1;
-                rd.skip(tot);
-                z += adv;
-            } while (z < 64 && rd.pos < stop);
+            adv = (MODE == BJ_M_DCFIRST) ? 64 : 1;
         }
+        rd.skip(tot);
+        z += adv;
         if (z >= 64) {
             z = 0;
             slot = (slot + 1 == nslots) ? 0 : slot + 1;
+            dct = c.dc_tab[slot];
+            act = c.ac_tab[slot];
         }
     }
 }
 
 // ---- baseline: writing pass ----------------------------------------------------------------------
-// Sink: begin(), put(zigzag_index, value), commit(block_in_stream) -- one whole block at a time.
+// Sink: begin(), put(zigzag_index, value), commit(block_in_stream, slot) -- one whole block at a time.
 // Returns BJ_ERR_* bits.  `blk` is the index (within the stream) of the first block this thread
-// owns; on return it is one past the last block written.
+// owns; on return it is one past the last block written.  If z != 0 on entry the open block belongs
+// to the previous subsequence: it is decoded without being written.
+// This loop is nested (per block: DC, AC symbols, commit) on purpose: the 24-instruction block flush
+// then runs with all lanes of the warp converged, which measured faster on B200 than the flat form
+// (2.8 vs 3.9 ms per 512 images) even though lanes wait for the block with the most symbols.
 template <class Src, class Sink>
 BJ_HD uint32_t base_write_run(BitReader<Src>& rd, int z, int slot, const ScanCtx& c, uint64_t stop, uint64_t stream_end,
                               uint32_t& blk, uint32_t nblk_stream, int pred[3], Sink& sink) {
     const uint32_t* const lut = c.lut;
     const int nslots = c.nslots;
-    // finish (without writing) the block that the previous subsequence started
     if (z != 0) {
         const uint32_t* const tab = lut + c.ac_tab[slot];
         while (z < 64) {

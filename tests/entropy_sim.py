@@ -33,7 +33,7 @@ def lib():
         _L.hs_decode_stream.restype = ctypes.c_uint32
         _L.hs_decode_stream.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                         ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p,
-                                        ctypes.c_void_p]
+                                        ctypes.c_void_p, ctypes.c_int]
         _L.hs_acrefine_stream.restype = ctypes.c_uint32
         _L.hs_acrefine_stream.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                           ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
@@ -61,7 +61,7 @@ def scan_block_list(p, sc):
     return out
 
 
-def decode_file(data: bytes, sub_bits: int = 1024, upto_scan=None):
+def decode_file(data: bytes, sub_bits: int = 1024, upto_scan=None, warm: int = 1):
     """Returns (parsed, per-component grids after each scan, stats per stream)."""
     L = lib()
     p = parse_jpeg(data)
@@ -102,7 +102,7 @@ def decode_file(data: bytes, sub_bits: int = 1024, upto_scan=None):
             stats = np.zeros(4, np.uint32)
             if sc.kind in ("baseline", "dc_first", "ac_first"):
                 err = L.hs_decode_stream(words.ctypes.data, len(words), int(starts[m]), int(ends[m]),
-                                         ctypes.byref(s), b_hi - b_lo, sub_bits, sub.ctypes.data, stats.ctypes.data)
+                                         ctypes.byref(s), b_hi - b_lo, sub_bits, sub.ctypes.data, stats.ctypes.data, warm)
                 all_stats.append(stats)
             elif sc.kind == "dc_refine":
                 L.hs_dcrefine_stream(words.ctypes.data, int(starts[m]), b_hi - b_lo, sc.al, sub.ctypes.data)

@@ -85,7 +85,7 @@ struct BlockSink {  // baseline: a whole block at a time
 //   [2] = fix-up rounds needed, [3] = total re-decodes in fix-up
 // Returns error bits.
 uint32_t hs_decode_stream(const uint32_t* words, uint64_t n_words, uint64_t start_byte, uint64_t end_byte,
-                          const SimScan* ss_, uint32_t nblk_stream, int sub_bits, int16_t* coef, uint32_t* stats) {
+                          const SimScan* ss_, uint32_t nblk_stream, int sub_bits, int16_t* coef, uint32_t* stats, int warm) {
     const SimScan& sc = *ss_;
     ScanCtx c = make_ctx(sc);
     HostSrc src{words, n_words};
@@ -119,7 +119,7 @@ uint32_t hs_decode_stream(const uint32_t* words, uint64_t n_words, uint64_t star
         else {
             uint64_t own = b0 + (uint64_t)l * S;
             BitReader<HostSrc> rd;
-            rd.seek(&src, own - S);
+            rd.seek(&src, own - S * (uint64_t)((uint32_t)warm < l ? (uint32_t)warm : l));
             int z = z0, slot = 0;
             SubCount k{0, {0, 0, 0}};
             if (sc.mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, c, ~0ull, own, b1, k);
