@@ -217,7 +217,8 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
 #define BJ_IN_SAMPLES 1  /* sample buffer produced by BJ_OUT_SAMPLES */
 
 int bj_version(void);
-int bj_sizeof(int what); /* 0: sizeof(bj_image), 1: sizeof(bj_scan), 2: sizeof(bj_entropy_buffers) */
+int bj_sizeof(int what);         /* 0: sizeof(bj_image) -- lets a binding verify its struct mirrors */
+int bj_sizeof_entropy(int what); /* 1: sizeof(bj_scan), 2: sizeof(bj_entropy_buffers) */
 const char* bj_last_cuda_error(void);
 
 /*
