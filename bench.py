@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images", type=int, default=4096, help="images per GPU per step")
+    ap.add_argument("--chunks", type=int, default=8, help="sub-batches per GPU, one CUDA stream each")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic images (cycled to --images)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="images decoded by the 1-core CPU baseline")
     args = ap.parse_args()
@@ -196,15 +197,25 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n_img = args.images
-    datas = [files[i % len(files)] for i in range(n_img)]
+    n_chunks = max(1, min(args.chunks, n_img))
     parsed_d = [parse_jpeg(d) for d in files]
-    parsed = [parsed_d[i % len(files)] for i in range(n_img)]
-    raw_host, offsets = pack_files(datas, pin=True)
-    plan = BatchPlan(parsed, offsets, raw_host.numel())
-    stream = torch.cuda.Stream(dev)
-    pipe = DevicePipeline(plan, dev, stream)
-    scan_bytes = int(plan.scans["raw_len"].sum())
-    nblk = plan.geom.total_blocks
+    # the batch is processed as n_chunks sub-batches, each with its own stream and buffers, so that the
+    # host->device copy of one sub-batch and the latency-bound kernels of another overlap
+    bounds = [round(i * n_img / n_chunks) for i in range(n_chunks + 1)]
+    pipes, raws = [], []
+    for c in range(n_chunks):
+        idx = range(bounds[c], bounds[c + 1])
+        datas = [files[i % len(files)] for i in idx]
+        parsed = [parsed_d[i % len(files)] for i in idx]
+        raw_host, offsets = pack_files(datas, pin=True)
+        plan = BatchPlan(parsed, offsets, raw_host.numel())
+        pipes.append(DevicePipeline(plan, dev, torch.cuda.Stream(dev)))
+        raws.append(raw_host)
+    main = torch.cuda.Stream(dev)
+    scan_bytes = int(sum(int(p.plan.scans["raw_len"].sum()) for p in pipes))
+    nblk = sum(p.plan.geom.total_blocks for p in pipes)
+    n_sub = sum(int(p.plan.n_sub) for p in pipes)
+    raw_bytes = sum(int(r.numel()) for r in raws)
     out_bytes = n_img * W * H * 3
     mp_per_step = n_img * W * H / 1e6
 
@@ -221,47 +232,67 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput (value) + per-stage times ---------------------------------------
-    pipe.upload(raw_host)
+    def timed_steps(n_steps, body):
+        """Run n_steps x body(pipe index) on the sub-batch streams, timed with CUDA events on `main`:
+        every stream starts after e0 and e1 is recorded after all of them have finished."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(main)
+        for p in pipes:
+            p.stream.wait_event(e0)
+        for _ in range(n_steps):
+            for c in range(len(pipes)):
+                body(c)
+        for p in pipes:
+            ev = torch.cuda.Event()
+            ev.record(p.stream)
+            main.wait_event(ev)
+        e1.record(main)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3 / n_steps
+        return max(e0.elapsed_time(e1) / n_steps, 0.0), wall
+
+    # ---- warm-up + correctness of the run ------------------------------------------------------------
+    for p, r in zip(pipes, raws):
+        p.upload(r)
     for _ in range(args.warmup):
-        pipe.launch()
+        for p in pipes:
+            p.launch()
     barrier()
-    raise_for_errors(pipe.err.cpu().numpy())
+    for p in pipes:
+        raise_for_errors(p.err.cpu().numpy())
+
+    # ---- per-stage times: sub-batches one after another, CUDA events around every stage --------------
+    events = {}
+    for _ in range(max(1, min(args.steps, 2))):
+        for p in pipes:
+            p.launch(events=events)
+            p.stream.synchronize()
+    stage_ms = {k: float(np.sum([a.elapsed_time(b) for (a, b) in v])) / max(1, min(args.steps, 2)) for k, v in events.items()}
+
+    # ---- device-resident throughput (value): all sub-batch streams concurrently -----------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    events = {}
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        pipe.launch(events=events)
-    e1.record(stream)
-    barrier()
-    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    stage_ms = {k: float(np.mean([a.elapsed_time(b) for (a, b) in v])) for k, v in events.items()}
+    ms_dev, _ = timed_steps(args.steps, lambda c: pipes[c].launch())
+    ms_dev = max_over_ranks(ms_dev)
 
     # ---- end to end: pinned host bytes -> device -> kernels -> status words back ---------------------
-    err_host = torch.empty(n_img, dtype=torch.int32, pin_memory=True)
-    for _ in range(max(1, args.warmup // 2)):
-        pipe.upload(raw_host)
-        pipe.launch()
-        with torch.cuda.stream(stream):
-            err_host.copy_(pipe.err, non_blocking=True)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    f0.record(stream)
-    for _ in range(args.steps):
-        pipe.upload(raw_host)
-        pipe.launch()
-        with torch.cuda.stream(stream):
-            err_host.copy_(pipe.err, non_blocking=True)
-    f1.record(stream)
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    ms_e2e = max_over_ranks(max(f0.elapsed_time(f1) / args.steps, wall_ms))
+    err_hosts = [torch.empty(len(p.plan.parsed), dtype=torch.int32, pin_memory=True) for p in pipes]
+
+    def e2e_body(c):
+        pipes[c].upload(raws[c])
+        pipes[c].launch()
+        with torch.cuda.stream(pipes[c].stream):
+            err_hosts[c].copy_(pipes[c].err, non_blocking=True)
+
+    timed_steps(max(1, args.warmup // 2), e2e_body)
+    ms_ev, ms_wall = timed_steps(args.steps, e2e_body)
+    ms_e2e = max_over_ranks(max(ms_ev, ms_wall))
     clocks = sampler.stop()
-    assert int(err_host.abs().sum()) == 0, "device reported decode errors"
+    assert all(int(e.abs().sum()) == 0 for e in err_hosts), "device reported decode errors"
+    launches_per_step = sum(p.kernel_launches_per_step for p in pipes)
+    device_bytes = sum(p.device_bytes() for p in pipes)
 
     if rank != 0:
         if world > 1:
@@ -270,7 +301,6 @@ def main():
 
     # ---- roofline accounting (algorithmic bytes) -------------------------------------
     peak, peak_src = measured_peak_gbs()
-    n_sub = int(plan.n_sub)
     alg = {
         "unstuff": 2 * scan_bytes,                       # read stuffed bytes, write compacted words
         "spec": scan_bytes + 32 * n_sub,                 # bitstream + entry/exit/count records
@@ -287,15 +317,25 @@ def main():
         else:
             stages[k] = {"ms": ms, "share_of_step": ms / sum(stage_ms.values())}
     dom = max((k for k in stages if "gbs" in stages[k]), key=lambda k: stages[k]["ms"])
-    roofline = {"kernel": {"unstuff": "unstuff_count/scan/scatter", "spec": "spec_kernel", "fix": "fix_kernel",
-                           "write": "write_kernel", "pixels": "bj_pixels_kernel"}[dom],
-                "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": stages[dom]["ms"]}
-    pix = stages.get("pixels", {})
-    roofline_pixels = {"kernel": "bj_pixels_kernel (fused dezigzag+dequant+IDCT+upsample+colour)", "bound": "hbm",
-                       "achieved": pix.get("gbs"), "peak": peak, "unit": "GB/s", "frac": pix.get("frac_of_peak"),
-                       "traffic": None}
+    # dram__bytes_read.sum + dram__bytes_write.sum per image from the ncu --set full captures under profiles/
+    # (r1b, 64 images per launch): measured DRAM traffic, scaled to the images one launch of this run covers
+    ncu_traffic_per_image = {"pixels": (402.810112e6 + 355.376896e6) / 64, "write": (30.704896e6 + 347.687424e6) / 64,
+                             "spec": 24.409856e6 / 64, "fix": 30.578176e6 / 64}
+    img_per_launch = n_img / n_chunks
+    names = {"unstuff": "unstuff_count/scan_tiles/unstuff_scatter", "spec": "spec_kernel", "fix": "fix_kernel",
+             "write": "write_kernel", "pixels": "bj_pixels_fast_kernel<2,2,3> (fused dezigzag+dequant+IDCT+upsample+colour)"}
+
+    def roof(k):
+        st = stages.get(k, {})
+        tr = ncu_traffic_per_image.get(k)
+        return {"kernel": names[k], "bound": "hbm", "achieved": st.get("gbs"), "peak": peak, "unit": "GB/s",
+                "frac": st.get("frac_of_peak"), "traffic": (tr * img_per_launch) if tr else None,
+                "traffic_source": "ncu --set full capture profiles/r1b_full_summary.csv, scaled per image",
+                "peak_source": peak_src, "launches_per_step": n_chunks,
+                "algorithmic_bytes_per_launch": alg[k] / n_chunks, "ms_per_launch": st.get("ms", 0.0) / n_chunks,
+                "share_of_step": st.get("share_of_step")}
+    roofline = roof(dom)
+    roofline_pixels = roof("pixels")
 
     # ---- CPU baseline: oracle port, one core, bounded sample ------------------------------------------
     cpu = None
@@ -317,17 +357,19 @@ def main():
         "data": f"synthetic: {len(files)} distinct Pillow-encoded 1080p images per GPU cycled to {n_img}",
         "config": {"workload": "batch of 4096 1920x1080 baseline 4:2:0 q75 JPEGs per GPU, no restart markers "
                                "(BASELINE.json configs[3])",
-                   "images_per_gpu": n_img, "l2": "inputs larger than L2 (bitstream %.2f GB, coefficients %.1f GB per step)"
-                                                  % (scan_bytes / 1e9, nblk * 128 / 1e9),
+                   "images_per_gpu": n_img, "sub_batches": n_chunks,
+                   "streams": "one CUDA stream per sub-batch; stage times measured with the sub-batches run one after another",
+                   "l2": "inputs larger than L2 (bitstream %.2f GB, coefficients %.1f GB per step)"
+                         % (scan_bytes / 1e9, nblk * 128 / 1e9),
                    "host_parse": "marker parsing and descriptor build happen before the timed region"},
         "e2e": {"value": mp_per_step * world / (ms_e2e * 1e-3), "unit": "MP/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(raw_host.numel()), "d2h_bytes_per_step": int(err_host.numel() * 4)},
-        "gpu_launches": pipe.kernel_launches_per_step * args.steps,
+                "h2d_bytes_per_step": raw_bytes, "d2h_bytes_per_step": 4 * n_img},
+        "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "roofline": roofline, "roofline_pixels": roofline_pixels, "stages": stages,
         "bitstream_gbs": {k: scan_bytes / (stage_ms[k] * 1e-3) / 1e9 for k in ("unstuff", "spec", "write") if k in stage_ms},
         "cpu_baseline": cpu,
-        "device_bytes": pipe.device_bytes(), "gen_seconds": t_gen,
+        "device_bytes": device_bytes, "gen_seconds": t_gen,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

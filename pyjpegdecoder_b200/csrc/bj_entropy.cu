@@ -66,6 +66,7 @@ struct CtaShared {
     uint32_t scan_nsub;
     uint32_t win_w0, win_n;
     uint32_t lut_cap;  // entries available in lut[] (dynamic shared memory)
+    uint32_t lut_in_smem;
     uint32_t win[kWinWords];
     uint32_t lut[1];   // lut_cap entries follow
 };
@@ -81,7 +82,7 @@ __device__ __forceinline__ void load_scan(CtaShared& sh, const bj_scan* scans, i
     if (in_smem)
         for (uint32_t i = threadIdx.x; i < sc.lut_len; i += blockDim.x) sh.lut[i] = __ldg(B.lut + sc.lut_off + i);
     if (threadIdx.x == 0) {
-        sh.ctx.lut = in_smem ? sh.lut : (B.lut + sc.lut_off);
+        sh.lut_in_smem = in_smem ? 1u : 0u;
         for (int i = 0; i < BJ_MAX_SLOTS; i++) {
             sh.ctx.dc_tab[i] = sc.slot_dc[i];
             sh.ctx.ac_tab[i] = sc.slot_ac[i];
@@ -104,7 +105,8 @@ struct SubInfo {
     uint32_t stream;     // absolute stream index
     uint32_t l;          // subsequence index inside the stream
     uint64_t b0, b1;     // stream bit range
-    uint64_t own, stop;  // own bit range
+    uint64_t own, stop;  // own bit range (absolute)
+    uint32_t own_rel, stop_rel, end_rel;  // the same relative to b0
     uint32_t nblk_stream;
     uint32_t mcu0;       // first MCU of the stream
 };
@@ -127,6 +129,9 @@ __device__ __forceinline__ SubInfo locate(const CtaShared& sh, const bj_entropy_
     s.b1 = B.stream_end[s.stream] * 8;
     s.own = s.b0 + (uint64_t)s.l * S;
     s.stop = min(s.own + (uint64_t)S, s.b1);
+    s.own_rel = s.l * S;
+    s.end_rel = (uint32_t)(s.b1 - s.b0);
+    s.stop_rel = min(s.own_rel + (uint32_t)S, s.end_rel);
     s.mcu0 = lo * sc.ri;
     uint32_t mcus = min(sc.ri, sc.n_mcu - s.mcu0);
     s.nblk_stream = mcus * sc.nslots;
@@ -153,25 +158,36 @@ __device__ __forceinline__ WinSrc win_src(const CtaShared& sh, const bj_entropy_
     return WinSrc{sh.win, sh.win_w0, sh.win_n, B.words, (uint32_t)B.words_len};
 }
 
-// Decode subsequence `si` from entry state st: exit state + counts.
-template <class Src>
-__device__ __forceinline__ void run_sub(const CtaShared& sh, const Src& src, const SubInfo& si, uint64_t st, uint64_t& ex,
-                                        SubCount& k) {
+// Decode subsequence `si` from entry state st: exit state + counts.  LUT_SMEM selects the shared-memory
+// copy of the scan's tables (compiles to LDS) or, for oversized tables, the global copy.
+template <bool LUT_SMEM, class Src>
+__device__ __forceinline__ void run_sub_impl(const CtaShared& sh, const uint32_t* __restrict__ glut, const Src& src,
+                                             uint64_t b0, uint32_t own_rel, uint32_t stop_rel, uint32_t end_rel, uint64_t st,
+                                             uint64_t& ex, SubCount& k) {
+    const uint32_t* lut = LUT_SMEM ? sh.lut : glut;
     BitReader<Src> rd;
-    rd.seek(&src, state_pos(st));
+    rd.seek(&src, b0, (uint32_t)(state_pos(st) - b0));
     int z = state_z(st), slot = state_slot(st);
     k.blocks = 0;
     k.dc[0] = k.dc[1] = k.dc[2] = 0;
     const int mode = sh.sc.mode;
-    if (mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, sh.ctx, si.own, si.stop, si.b1, k);
-    else if (mode == BJ_MODE_DC_FIRST) sync_run<BJ_M_DCFIRST>(rd, z, slot, sh.ctx, si.own, si.stop, si.b1, k);
+    if (mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, sh.ctx, lut, own_rel, stop_rel, end_rel, k);
+    else if (mode == BJ_MODE_DC_FIRST) sync_run<BJ_M_DCFIRST>(rd, z, slot, sh.ctx, lut, own_rel, stop_rel, end_rel, k);
     else {
         struct NoSink { __device__ void store(uint32_t, int, int16_t) {} } ns;
         uint32_t blk = 0, adv = 0;
-        acfirst_run<false>(rd, z, sh.ctx, si.own, si.stop, si.b1, blk, 0xFFFFFFFFu, adv, ns);
+        acfirst_run<false>(rd, z, sh.ctx, lut, own_rel, stop_rel, end_rel, blk, 0xFFFFFFFFu, adv, ns);
         k.blocks = adv;
     }
-    ex = pack_state(rd.pos, z, slot);
+    ex = pack_state(rd.abs_pos(), z, slot);
+}
+
+template <class Src>
+__device__ __forceinline__ void run_sub(const CtaShared& sh, const bj_entropy_buffers& B, const Src& src, uint64_t b0,
+                                        uint32_t own_rel, uint32_t stop_rel, uint32_t end_rel, uint64_t st, uint64_t& ex,
+                                        SubCount& k) {
+    if (sh.lut_in_smem) run_sub_impl<true>(sh, nullptr, src, b0, own_rel, stop_rel, end_rel, st, ex, k);
+    else run_sub_impl<false>(sh, B.lut + sh.sc.lut_off, src, b0, own_rel, stop_rel, end_rel, st, ex, k);
 }
 
 // ---- plan ------------------------------------------------------------------------------------------
@@ -242,17 +258,14 @@ __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ sca
     uint64_t st;
     if (si.l == 0) st = pack_state(si.b0, z0, 0);
     else {
-        SubInfo warm = si;
-        warm.own = ~0ull;  // nothing is counted while warming up
-        warm.stop = si.own;
         uint64_t ex;
-        SubCount k;
-        run_sub(sh, src, warm, pack_state(si.own - S, z0, 0), ex, k);
+        SubCount k;  // nothing is counted while warming up (own_rel = 0xFFFFFFFF)
+        run_sub(sh, B, src, si.b0, 0xFFFFFFFFu, si.own_rel, si.end_rel, pack_state(si.own - S, z0, 0), ex, k);
         st = ex;
     }
     uint64_t ex;
     SubCount k;
-    run_sub(sh, src, si, st, ex, k);
+    run_sub(sh, B, src, si.b0, si.own_rel, si.stop_rel, si.end_rel, st, ex, k);
     const size_t g = (size_t)sh.sc.sub0 + lscan;
     B.sub_entry[g] = st;
     B.sub_exit[g] = ex;
@@ -268,7 +281,8 @@ __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scan
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
     __shared__ uint64_t s_entry[T], s_exit[T];
-    __shared__ uint64_t s_own[T], s_stop[T], s_b1[T];
+    __shared__ uint64_t s_b0[T];
+    __shared__ uint32_t s_ownr[T], s_stopr[T], s_endr[T];
     __shared__ uint32_t s_cnt[T][4];
     __shared__ uint32_t s_head[T];
     __shared__ uint16_t s_list[T];
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scan
         s_entry[tid] = entry;
         s_exit[tid] = ex;
         s_cnt[tid][0] = c.x; s_cnt[tid][1] = c.y; s_cnt[tid][2] = c.z; s_cnt[tid][3] = c.w;
-        s_own[tid] = si.own; s_stop[tid] = si.stop; s_b1[tid] = si.b1;
+        s_b0[tid] = si.b0; s_ownr[tid] = si.own_rel; s_stopr[tid] = si.stop_rel; s_endr[tid] = si.end_rel;
     }
     const bool head = si.valid && si.l == 0;          // entry state known exactly
     const bool needs_prev_cta = (tid == 0) && si.valid && !head;
@@ -338,11 +352,9 @@ __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scan
             __syncthreads();
             if ((uint32_t)tid < total) {  // dense: item i is decoded by thread i
                 const int j = s_list[tid];
-                SubInfo sj;
-                sj.own = s_own[j]; sj.stop = s_stop[j]; sj.b1 = s_b1[j];
                 uint64_t ex;
                 SubCount k;
-                run_sub(sh, src, sj, s_entry[j], ex, k);
+                run_sub(sh, B, src, s_b0[j], s_ownr[j], s_stopr[j], s_endr[j], s_entry[j], ex, k);
                 s_exit[j] = ex;
                 s_cnt[j][0] = k.blocks; s_cnt[j][1] = (uint32_t)k.dc[0]; s_cnt[j][2] = (uint32_t)k.dc[1]; s_cnt[j][3] = (uint32_t)k.dc[2];
                 changes++;
@@ -506,22 +518,26 @@ __global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ sc
     const uint64_t st = B.sub_entry[g];
     const uint4 pre = reinterpret_cast<const uint4*>(B.sub_prefix)[g];
     BitReader<WinSrc> rd;
-    rd.seek(&src, state_pos(st));
+    rd.seek(&src, si.b0, (uint32_t)(state_pos(st) - si.b0));
     int z = state_z(st), slot = state_slot(st);
     uint32_t blk = pre.x;
     int pred[3] = {(int)pre.y, (int)pre.z, (int)pre.w};
     uint32_t err = 0;
     const int mode = sh.sc.mode;
+    const bool ls = sh.lut_in_smem != 0;
+    const uint32_t* glut = B.lut + sh.sc.lut_off;
     if (mode == BJ_MODE_BASELINE) {
         SmemBlockSink sink{reinterpret_cast<unsigned char*>(s_blocks) + tid * 16, B.coef, &sh.sc, si.mcu0};
-        err = base_write_run(rd, z, slot, sh.ctx, si.stop, si.b1, blk, si.nblk_stream, pred, sink);
+        if (ls) err = base_write_run(rd, z, slot, sh.ctx, sh.lut, si.stop_rel, si.end_rel, blk, si.nblk_stream, pred, sink);
+        else err = base_write_run(rd, z, slot, sh.ctx, glut, si.stop_rel, si.end_rel, blk, si.nblk_stream, pred, sink);
     } else if (mode == BJ_MODE_DC_FIRST) {
         GlobalCoefSink sink{B.coef, &sh.sc, si.mcu0};
-        err = dcfirst_write_run(rd, slot, sh.ctx, si.stop, si.b1, blk, si.nblk_stream, pred, sink);
+        err = dcfirst_write_run(rd, slot, sh.ctx, ls ? sh.lut : glut, si.stop_rel, si.end_rel, blk, si.nblk_stream, pred, sink);
     } else {
         GlobalCoefSink sink{B.coef, &sh.sc, si.mcu0};
         uint32_t adv = 0;
-        err = acfirst_run<true>(rd, z, sh.ctx, si.own, si.stop, si.b1, blk, si.nblk_stream, adv, sink);
+        err = acfirst_run<true>(rd, z, sh.ctx, ls ? sh.lut : glut, si.own_rel, si.stop_rel, si.end_rel, blk, si.nblk_stream, adv,
+                                sink);
     }
     // the last subsequence of a stream checks that the stream held all its blocks
     if (si.stop == si.b1) {
@@ -569,11 +585,12 @@ __global__ void __launch_bounds__(32) acrefine_kernel(const bj_scan* __restrict_
     if (m >= sc.n_streams) return;
     GlobalSrc src{B.words, (uint32_t)B.words_len};
     BitReader<GlobalSrc> rd;
-    rd.seek(&src, B.stream_start[sc.stream0 + m] * 8);
+    const uint64_t sb0 = B.stream_start[sc.stream0 + m] * 8, sb1 = B.stream_end[sc.stream0 + m] * 8;
+    rd.seek(&src, sb0, 0);
     const uint32_t mcu0 = m * sc.ri;
     const uint32_t nblk = min(sc.ri, sc.n_mcu - mcu0);
     GlobalCoefRef cf{B.coef, &sc, mcu0};
-    uint32_t err = acrefine_stream(rd, sh.ctx, B.stream_end[sc.stream0 + m] * 8, nblk, cf);
+    uint32_t err = acrefine_stream(rd, sh.ctx, sh.lut_in_smem ? sh.lut : (B.lut + sc.lut_off), (uint32_t)(sb1 - sb0), nblk, cf);
     if (err) atomicOr(&B.err[sc.image], err);
 }
 

@@ -39,19 +39,23 @@ BJ_HD int state_z(uint64_t s) { return (int)((s >> 44) & 127); }
 BJ_HD int state_slot(uint64_t s) { return (int)((s >> 51) & 15); }
 
 // ---- Huffman LUT entry (built by pyjpegdecoder_b200/huffman.py) ----------------------------------
-// direct:   bits 0..7 symbol, 8..12 code length L (0 = no such code), 13..17 L + (symbol & 15),
-//           18..24 zig-zag advance for baseline AC (run + 1; 64 for EOB; 16 for ZRL)
-// indirect: bit 31 set, bits 0..15 offset of a 128-entry second-level table (relative to the table)
+// Fields are byte aligned so that each one is a single LOP/PRMT on the device:
+//   direct:   byte 0 = L + (symbol & 15) (bits consumed by code + value; bit 7 clear)
+//             byte 1 = zig-zag advance for baseline AC (run + 1; 64 for EOB; 16 for ZRL; 1 for DC)
+//             byte 2 = code length L (0 = no such code; such entries have byte 0 = byte 1 = 1 so that a
+//                      speculating decoder still makes progress)
+//             byte 3 = symbol
+//   indirect: bit 7 set, bits 8..23 = offset of a 128-entry second-level table (relative to the table)
 // first level: 512 entries indexed by the next 9 bits; second level by the following 7 bits.
 BJ_HD uint32_t lut_lookup(const uint32_t* tab, uint32_t peek16) {
     uint32_t e = tab[peek16 >> 7];
-    if (e & 0x80000000u) e = tab[(e & 0xFFFFu) + (peek16 & 127u)];
+    if (e & 0x80u) e = tab[((e >> 8) & 0xFFFFu) + (peek16 & 127u)];
     return e;
 }
-BJ_HD int ent_sym(uint32_t e) { return (int)(e & 255u); }
-BJ_HD int ent_len(uint32_t e) { return (int)((e >> 8) & 31u); }
-BJ_HD int ent_total(uint32_t e) { return (int)((e >> 13) & 31u); }
-BJ_HD int ent_adv(uint32_t e) { return (int)((e >> 18) & 127u); }
+BJ_HD int ent_total(uint32_t e) { return (int)(e & 0xFFu); }
+BJ_HD int ent_adv(uint32_t e) { return (int)((e >> 8) & 0xFFu); }
+BJ_HD int ent_len(uint32_t e) { return (int)((e >> 16) & 0xFFu); }
+BJ_HD int ent_sym(uint32_t e) { return (int)(e >> 24); }
 
 // EXTEND (bin_twos_complement, :1636-1646)
 BJ_HD int extend(uint32_t v, int n) { return (n == 0) ? 0 : ((v >> (n - 1)) ? (int)v : (int)v - ((1 << n) - 1)); }
@@ -74,24 +78,28 @@ struct BitReader {
     uint32_t w0, w1;  // current and next word
     int o;            // bits of w0 consumed (0..31)
     uint32_t next;    // next word to fetch
-    uint64_t pos;     // absolute bit position
+    uint32_t rel;     // bit position relative to `base` (a stream is far below 2^32 bits)
+    uint64_t base;    // absolute bit position of the stream start
 
-    BJ_HDM void seek(const Src* s, uint64_t p) {
+    BJ_HDM void seek(const Src* s, uint64_t base_bit, uint32_t rel_bit) {
         src = s;
-        pos = p;
+        base = base_bit;
+        rel = rel_bit;
+        const uint64_t p = base_bit + rel_bit;
         uint32_t w = (uint32_t)(p >> 5);
         o = (int)(p & 31);
         w0 = src->word(w);
         w1 = src->word(w + 1);
         next = w + 2;
     }
+    BJ_HDM uint64_t abs_pos() const { return base + rel; }
     BJ_HDM uint32_t peek32() const { return funnel_left(w0, w1, o); }
     BJ_HDM uint32_t peek16() const { return peek32() >> 16; }
     // n bits (1..16) that follow the first `skipn` bits (skipn + n <= 32)
     BJ_HDM uint32_t bits_after(int skipn, int n) const { return (peek32() << skipn) >> (32 - n); }
     BJ_HDM void skip(int n) {  // n <= 32
         o += n;
-        pos += (uint64_t)n;
+        rel += (uint32_t)n;
         if (o >= 32) {
             o -= 32;
             w0 = w1;
@@ -105,7 +113,6 @@ BJ_HD uint32_t take_bits(uint32_t pk, int skipn, int n) { return (pk << skipn) >
 
 // ---- per-scan context (shared memory on the device) ----------------------------------------------
 struct ScanCtx {
-    const uint32_t* lut;              // this scan's LUT blob
     uint16_t dc_tab[BJ_MAX_SLOTS];    // table offsets inside the blob
     uint16_t ac_tab[BJ_MAX_SLOTS];
     uint8_t slot_comp[BJ_MAX_SLOTS];  // slot -> DC predictor index
@@ -118,13 +125,13 @@ struct SubCount {
     int32_t dc[3];    // sum of DC differences per scan component
 };
 
-// True when the bits from pos to the end of the stream are only the 1-padding of the last byte
-// (fewer than 8 bits, all ones): no Huffman code consists of ones only, so real data never looks
-// like this.
+// True when the bits from the reader's position to the end of the stream (end_rel, same base) are only
+// the 1-padding of the last byte (fewer than 8 bits, all ones): no Huffman code consists of ones only,
+// so real data never looks like this.
 template <class Src>
-BJ_HD bool at_padding(const BitReader<Src>& rd, uint64_t stream_end) {
-    if (rd.pos >= stream_end) return true;
-    uint64_t left = stream_end - rd.pos;
+BJ_HD bool at_padding(const BitReader<Src>& rd, uint32_t end_rel) {
+    if (rd.rel >= end_rel) return true;
+    uint32_t left = end_rel - rd.rel;
     if (left >= 8) return false;
     uint32_t ones = (1u << left) - 1u;
     return rd.bits_after(0, (int)left) == ones;
@@ -133,31 +140,34 @@ BJ_HD bool at_padding(const BitReader<Src>& rd, uint64_t stream_end) {
 #define BJ_M_BASE 0
 #define BJ_M_DCFIRST 1
 
+// All positions below are 32-bit and relative to the stream start (rd.base): own_rel = first bit of
+// the subsequence (0xFFFFFFFF: count nothing), stop_rel = its end, end_rel = end of the stream.
+// `lut` is the scan's LUT blob; it is a separate argument (not a field of ScanCtx) so that the CUDA
+// compiler can see when it points to shared memory and emit LDS instead of generic loads.
+
 // ---- baseline / DC-first: counting pass ----------------------------------------------------------
-// Decode from (rd.pos, z, slot) until rd.pos >= stop.  Blocks whose DC symbol starts at a position
-// >= own_start are counted and their DC differences summed.  Nothing is written.
-// The loops below are FLAT: every iteration decodes exactly one symbol (DC or AC, chosen by a table
-// select), so the 32 lanes of a warp stay converged even though their blocks have different numbers
-// of symbols; only the short DC / end-of-block bodies diverge.
+// Decode from the reader's position with state (z, slot) until rd.rel >= stop_rel.  Blocks whose DC
+// symbol starts at a position >= own_rel are counted and their DC differences summed.  Nothing is
+// written.  FLAT loop: every iteration decodes exactly one symbol (DC or AC, chosen by a table
+// select), so the 32 lanes of a warp stay converged although their blocks have different numbers of
+// symbols; only the short DC / end-of-block bodies diverge.
 template <int MODE, class Src>
-BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, uint64_t own_start, uint64_t stop,
-                    uint64_t stream_end, SubCount& cnt) {
-    const uint32_t* const lut = c.lut;
+BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, const uint32_t* lut, uint32_t own_rel,
+                    uint32_t stop_rel, uint32_t end_rel, SubCount& cnt) {
     const int nslots = c.nslots;
     uint32_t dct = c.dc_tab[slot], act = c.ac_tab[slot];
-    while (rd.pos < stop) {
+    while (rd.rel < stop_rel) {
         const bool is_dc = (z == 0);
-        if (is_dc && stream_end - rd.pos < 8 && at_padding(rd, stream_end)) {
-            rd.pos = stream_end;
+        if (is_dc && end_rel - rd.rel < 8 && at_padding(rd, end_rel)) {
+            rd.rel = end_rel;
             break;
         }
         const uint32_t pk = rd.peek32();
         const uint32_t e = lut_lookup(lut + (is_dc ? dct : act), pk >> 16);
-        const int L = ent_len(e);
-        int tot = ent_total(e), adv = ent_adv(e);
-        if (L == 0) { tot = 1; adv = 1; }  // not a code: any deterministic step will do while speculating
+        int adv = ent_adv(e);
         if (is_dc) {
-            if (rd.pos >= own_start) {
+            if (rd.rel >= own_rel) {
+                const int L = ent_len(e);
                 const int t = L ? ent_sym(e) : 0;
                 cnt.blocks++;
                 int diff = extend(t ? take_bits(pk, L, t) : 0u, t);
@@ -168,7 +178,7 @@ BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, uin
             }
             adv = (MODE == BJ_M_DCFIRST) ? 64 : 1;
         }
-        rd.skip(tot);
+        rd.skip(ent_total(e));  // entries that are not a code consume 1 bit: any deterministic step will do
         z += adv;
         if (z >= 64) {
             z = 0;
@@ -188,28 +198,30 @@ BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, uin
 // then runs with all lanes of the warp converged, which measured faster on B200 than the flat form
 // (2.8 vs 3.9 ms per 512 images) even though lanes wait for the block with the most symbols.
 template <class Src, class Sink>
-BJ_HD uint32_t base_write_run(BitReader<Src>& rd, int z, int slot, const ScanCtx& c, uint64_t stop, uint64_t stream_end,
-                              uint32_t& blk, uint32_t nblk_stream, int pred[3], Sink& sink) {
-    const uint32_t* const lut = c.lut;
+BJ_HD uint32_t base_write_run(BitReader<Src>& rd, int z, int slot, const ScanCtx& c, const uint32_t* lut, uint32_t stop_rel,
+                              uint32_t end_rel, uint32_t& blk, uint32_t nblk_stream, int pred[3], Sink& sink) {
+    // Single-exit loops only (errors are carried in `err`, never returned from inside a loop): the
+    // compiler then reconverges the warp after every inner loop, which this nested form relies on.
     const int nslots = c.nslots;
+    uint32_t err = 0;
     if (z != 0) {
         const uint32_t* const tab = lut + c.ac_tab[slot];
         while (z < 64) {
-            if (rd.pos >= stream_end + 64) return BJ_ERR_OVERRUN;
             uint32_t e = lut_lookup(tab, rd.peek16());
-            if (ent_len(e) == 0) return BJ_ERR_BAD_CODE;
+            if (ent_len(e) == 0) err |= BJ_ERR_BAD_CODE;
+            if (rd.rel >= end_rel + 64) err |= BJ_ERR_OVERRUN;
             rd.skip(ent_total(e));
-            z += ent_adv(e);
+            z += err ? 64 : ent_adv(e);
         }
         slot = (slot + 1 == nslots) ? 0 : slot + 1;
     }
-    while (rd.pos < stop && blk < nblk_stream) {
+    while (err == 0 && rd.rel < stop_rel && blk < nblk_stream) {
         sink.begin();
         {
             const uint32_t pk = rd.peek32();
             uint32_t e = lut_lookup(lut + c.dc_tab[slot], pk >> 16);
             int L = ent_len(e), t = ent_sym(e);
-            if (L == 0) return BJ_ERR_BAD_CODE;
+            if (L == 0) { err |= BJ_ERR_BAD_CODE; t = 0; }
             int diff = extend(t ? take_bits(pk, L, t) : 0u, t);
             int k = c.slot_comp[slot];
             int pv;
@@ -225,28 +237,30 @@ BJ_HD uint32_t base_write_run(BitReader<Src>& rd, int z, int slot, const ScanCtx
             const uint32_t pk = rd.peek32();
             uint32_t e = lut_lookup(tab, pk >> 16);
             int L = ent_len(e), tot = ent_total(e);
-            if (L == 0) return BJ_ERR_BAD_CODE;
             int s = tot - L;
             zz += ent_adv(e) - 1;  // zero run (EOB: jumps past 63, ZRL: 15)
+            if (L == 0) { err |= BJ_ERR_BAD_CODE; zz = 64; }
             if (s && zz < 64) sink.put(zz, (int16_t)extend(take_bits(pk, L, s), s));
             rd.skip(tot);
             zz++;
         }
-        if (rd.pos > stream_end + 7) return BJ_ERR_OVERRUN;
-        sink.commit(blk, slot);
-        blk++;
+        if (rd.rel > end_rel + 7) err |= BJ_ERR_OVERRUN;
+        if (err == 0) {
+            sink.commit(blk, slot);
+            blk++;
+        }
         slot = (slot + 1 == nslots) ? 0 : slot + 1;
     }
-    return 0;
+    return err;
 }
 
 // ---- DC first: writing pass (one 16-bit store per block) -----------------------------------------
 template <class Src, class Sink>
-BJ_HD uint32_t dcfirst_write_run(BitReader<Src>& rd, int slot, const ScanCtx& c, uint64_t stop, uint64_t stream_end,
-                                 uint32_t& blk, uint32_t nblk_stream, int pred[3], Sink& sink) {
-    while (rd.pos < stop && blk < nblk_stream) {
+BJ_HD uint32_t dcfirst_write_run(BitReader<Src>& rd, int slot, const ScanCtx& c, const uint32_t* lut, uint32_t stop_rel,
+                                 uint32_t end_rel, uint32_t& blk, uint32_t nblk_stream, int pred[3], Sink& sink) {
+    while (rd.rel < stop_rel && blk < nblk_stream) {
         const uint32_t pk = rd.peek32();
-        uint32_t e = lut_lookup(c.lut + c.dc_tab[slot], pk >> 16);
+        uint32_t e = lut_lookup(lut + c.dc_tab[slot], pk >> 16);
         int L = ent_len(e), t = ent_sym(e);
         if (L == 0) return BJ_ERR_BAD_CODE;
         int diff = extend(t ? take_bits(pk, L, t) : 0u, t);
@@ -256,7 +270,7 @@ BJ_HD uint32_t dcfirst_write_run(BitReader<Src>& rd, int slot, const ScanCtx& c,
         else if (k == 1) pv = (pred[1] += diff);
         else pv = (pred[2] += diff);
         rd.skip(ent_total(e));
-        if (rd.pos > stream_end + 7) return BJ_ERR_OVERRUN;
+        if (rd.rel > end_rel + 7) return BJ_ERR_OVERRUN;
         sink.store_dc(blk, slot, (int16_t)((uint32_t)(int32_t)(int16_t)pv << c.al));  // (:1029)
         blk++;
         slot = (slot + 1 == c.nslots) ? 0 : slot + 1;
@@ -268,20 +282,22 @@ BJ_HD uint32_t dcfirst_write_run(BitReader<Src>& rd, int slot, const ScanCtx& c,
 // State: zig-zag index z in [ss, se].  A symbol either places a coefficient after a zero run, skips
 // 16 zeros (ZRL), or ends the band of this block and of the next EOBRUN-1 blocks.  WRITE = false:
 // count block advance only; WRITE = true: also store coefficients of symbols that start at or
-// after own_start (symbol-level ownership; the planes were zeroed before the first scan).
+// after own_rel (symbol-level ownership; the planes were zeroed before the first scan).
 template <bool WRITE, class Src, class Sink>
-BJ_HD uint32_t acfirst_run(BitReader<Src>& rd, int& z, const ScanCtx& c, uint64_t own_start, uint64_t stop,
-                           uint64_t stream_end, uint32_t& blk, uint32_t nblk_stream, uint32_t& advance, Sink& sink) {
-    const uint32_t* tab = c.lut + c.ac_tab[0];
-    while (rd.pos < stop) {
+BJ_HD uint32_t acfirst_run(BitReader<Src>& rd, int& z, const ScanCtx& c, const uint32_t* lut, uint32_t own_rel,
+                           uint32_t stop_rel, uint32_t end_rel, uint32_t& blk, uint32_t nblk_stream, uint32_t& advance,
+                           Sink& sink) {
+    const uint32_t* tab = lut + c.ac_tab[0];
+    while (rd.rel < stop_rel) {
         if (WRITE && blk >= nblk_stream) break;
-        if (stream_end - rd.pos < 8 && at_padding(rd, stream_end)) {
-            rd.pos = stream_end;
+        if (end_rel - rd.rel < 8 && at_padding(rd, end_rel)) {
+            rd.rel = end_rel;
             break;
         }
-        uint32_t e = lut_lookup(tab, rd.peek16());
+        const uint32_t pk = rd.peek32();
+        uint32_t e = lut_lookup(tab, pk >> 16);
         int L = ent_len(e), rs = ent_sym(e);
-        bool own = rd.pos >= own_start;
+        bool own = rd.rel >= own_rel;
         if (L == 0) {
             if (WRITE) return BJ_ERR_BAD_CODE;
             rd.skip(1);
@@ -293,7 +309,7 @@ BJ_HD uint32_t acfirst_run(BitReader<Src>& rd, int& z, const ScanCtx& c, uint64_
             z += r;
             if (WRITE && own) {
                 if (z > 63) return BJ_ERR_COEF_INDEX;
-                sink.store(blk, z, (int16_t)((uint32_t)extend(rd.bits_after(L, s), s) << c.al));  // (:1225)
+                sink.store(blk, z, (int16_t)((uint32_t)extend(take_bits(pk, L, s), s) << c.al));  // (:1225)
             }
             z++;
             rd.skip(L + s);
@@ -301,7 +317,7 @@ BJ_HD uint32_t acfirst_run(BitReader<Src>& rd, int& z, const ScanCtx& c, uint64_
             z += 16;  // (:1142-1143)
             rd.skip(L);
         } else {
-            uint32_t run = (1u << r) + (r ? rd.bits_after(L, r) : 0u);  // (:1144-1149)
+            uint32_t run = (1u << r) + (r ? take_bits(pk, L, r) : 0u);  // (:1144-1149)
             rd.skip(L + r);
             adv = run;
             z = c.ss;
@@ -322,16 +338,18 @@ BJ_HD uint32_t acfirst_run(BitReader<Src>& rd, int& z, const ScanCtx& c, uint64_
 // Correction is the reference's `coef |= bit << Al` on the two's-complement value (:1114), which is
 // NOT the T.81 rule for negative coefficients; bit-exact parity with the reference requires it.
 template <class Src, class Coef>
-BJ_HD uint32_t acrefine_stream(BitReader<Src>& rd, const ScanCtx& c, uint64_t stream_end, uint32_t nblk_stream, Coef& coef) {
-    const uint32_t* tab = c.lut + c.ac_tab[0];
+BJ_HD uint32_t acrefine_stream(BitReader<Src>& rd, const ScanCtx& c, const uint32_t* lut, uint32_t end_rel,
+                               uint32_t nblk_stream, Coef& coef) {
+    const uint32_t* tab = lut + c.ac_tab[0];
     const int ss = c.ss, se = c.se, al = c.al;
     uint32_t blk = 0;
     while (blk < nblk_stream) {
         int z = ss;
         uint32_t eob_run = 0;
         while (z <= se) {
-            if (rd.pos > stream_end + 7) return BJ_ERR_OVERRUN;
-            uint32_t e = lut_lookup(tab, rd.peek16());
+            if (rd.rel > end_rel + 7) return BJ_ERR_OVERRUN;
+            const uint32_t pk = rd.peek32();
+            uint32_t e = lut_lookup(tab, pk >> 16);
             int L = ent_len(e), rs = ent_sym(e);
             if (L == 0) return BJ_ERR_BAD_CODE;
             int r = rs >> 4, s = rs & 15;
@@ -345,12 +363,12 @@ BJ_HD uint32_t acrefine_stream(BitReader<Src>& rd, const ScanCtx& c, uint64_t st
                 rd.skip(L);
                 zero_run = 16;
             } else if (s == 0) {
-                eob_run = (1u << r) + (r ? rd.bits_after(L, r) : 0u);
+                eob_run = (1u << r) + (r ? take_bits(pk, L, r) : 0u);
                 rd.skip(L + r);
                 break;
             } else {
                 zero_run = r;
-                newval = extend(rd.bits_after(L, s), s);  // value bits come right after the code (:1202)
+                newval = extend(take_bits(pk, L, s), s);  // value bits come right after the code (:1202)
                 rd.skip(L + s);
             }
             // skip `zero_run` zero-history coefficients, refining the non-zero ones passed (:1184-1193);
@@ -389,7 +407,7 @@ BJ_HD uint32_t acrefine_stream(BitReader<Src>& rd, const ScanCtx& c, uint64_t st
             for (; z <= se; z++) {
                 int16_t& cf = coef.at(blk, z);
                 if (cf != 0) {
-                    if (rd.pos > stream_end + 7) return BJ_ERR_OVERRUN;
+                    if (rd.rel > end_rel + 7) return BJ_ERR_OVERRUN;
                     cf = (int16_t)(cf | (int16_t)(rd.bits_after(0, 1) << al));
                     rd.skip(1);
                 }

@@ -16,6 +16,8 @@ from .parser import HuffSpec
 
 L1_BITS = 9
 L2_BITS = 16 - L1_BITS
+# not a code: length 0, but consumes 1 bit and advances 1 so that a speculating decoder makes progress
+INVALID_ENTRY = 1 | (1 << 8)
 
 
 def canonical_codes(spec: HuffSpec) -> List[Tuple[int, int, int]]:
@@ -37,7 +39,7 @@ def canonical_codes(spec: HuffSpec) -> List[Tuple[int, int, int]]:
 @lru_cache(maxsize=4096)
 def build_table(spec: HuffSpec, is_dc: bool) -> np.ndarray:
     """uint32 LUT for one table: 512 first-level entries + 128 per second-level table."""
-    l1 = np.zeros(1 << L1_BITS, np.uint32)
+    l1 = np.full(1 << L1_BITS, INVALID_ENTRY, np.uint32)
     subs: List[np.ndarray] = []
     sub_of_prefix: Dict[int, int] = {}
     for code, length, sym in canonical_codes(spec):
@@ -53,7 +55,7 @@ def build_table(spec: HuffSpec, is_dc: bool) -> np.ndarray:
         if total > 31:
             # cannot happen for length <= 16 and size <= 15
             continue
-        entry = sym | (length << 8) | (total << 13) | (adv << 18)
+        entry = total | (adv << 8) | (length << 16) | (sym << 24)
         if length <= L1_BITS:
             lo = code << (L1_BITS - length)
             l1[lo:lo + (1 << (L1_BITS - length))] = entry
@@ -62,7 +64,7 @@ def build_table(spec: HuffSpec, is_dc: bool) -> np.ndarray:
             prefix = code16 >> L2_BITS
             if prefix not in sub_of_prefix:
                 sub_of_prefix[prefix] = len(subs)
-                subs.append(np.zeros(1 << L2_BITS, np.uint32))
+                subs.append(np.full(1 << L2_BITS, INVALID_ENTRY, np.uint32))
             sub = subs[sub_of_prefix[prefix]]
             lo = code16 & ((1 << L2_BITS) - 1)
             sub[lo:lo + (1 << (16 - length))] = entry
@@ -70,13 +72,13 @@ def build_table(spec: HuffSpec, is_dc: bool) -> np.ndarray:
         off = (1 << L1_BITS) + si * (1 << L2_BITS)
         if off > 0xFFFF:
             raise CorruptedJpeg("Huffman table too irregular for the device tables.")
-        l1[prefix] = 0x80000000 | off
+        l1[prefix] = 0x80 | (off << 8)
     t = np.concatenate([l1] + subs) if subs else l1
     t.setflags(write=False)
     return t
 
 
-_EMPTY = np.zeros(1 << L1_BITS, np.uint32)
+_EMPTY = np.full(1 << L1_BITS, INVALID_ENTRY, np.uint32)
 
 
 def build_scan_blob(dc_specs: Sequence, ac_specs: Sequence) -> Tuple[np.ndarray, List[int], List[int]]:

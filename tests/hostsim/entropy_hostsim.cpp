@@ -56,7 +56,6 @@ struct SimScan {
 
 static ScanCtx make_ctx(const SimScan& s) {
     ScanCtx c;
-    c.lut = s.lut;
     for (int i = 0; i < BJ_MAX_SLOTS; i++) {
         c.dc_tab[i] = s.dc_tab[i];
         c.ac_tab[i] = s.ac_tab[i];
@@ -96,39 +95,40 @@ uint32_t hs_decode_stream(const uint32_t* words, uint64_t n_words, uint64_t star
     std::vector<uint64_t> entry(nsub), exitst(nsub);
     std::vector<SubCount> cnt(nsub);
     BlockSink dummy{};
+    const uint32_t nbits = (uint32_t)(b1 - b0);
     auto run_sub = [&](uint32_t l, uint64_t st) {  // decode subsequence l from entry state st -> exit state, counts
-        uint64_t own = b0 + (uint64_t)l * S, stop = own + S < b1 ? own + S : b1;
+        uint32_t own = l * (uint32_t)S, stop = own + (uint32_t)S < nbits ? own + (uint32_t)S : nbits;
         BitReader<HostSrc> rd;
-        rd.seek(&src, state_pos(st));
+        rd.seek(&src, b0, (uint32_t)(state_pos(st) - b0));
         int z = state_z(st), slot = state_slot(st);
         SubCount k{0, {0, 0, 0}};
-        if (sc.mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, c, own, stop, b1, k);
-        else if (sc.mode == BJ_MODE_DC_FIRST) sync_run<BJ_M_DCFIRST>(rd, z, slot, c, own, stop, b1, k);
+        if (sc.mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, c, sc.lut, own, stop, nbits, k);
+        else if (sc.mode == BJ_MODE_DC_FIRST) sync_run<BJ_M_DCFIRST>(rd, z, slot, c, sc.lut, own, stop, nbits, k);
         else {
             uint32_t blk = 0, adv = 0;
-            acfirst_run<false>(rd, z, c, own, stop, b1, blk, 0xFFFFFFFFu, adv, dummy);
+            acfirst_run<false>(rd, z, c, sc.lut, own, stop, nbits, blk, 0xFFFFFFFFu, adv, dummy);
             k.blocks = adv;
         }
         cnt[l] = k;
-        exitst[l] = pack_state(rd.pos, z, slot);
+        exitst[l] = pack_state(rd.abs_pos(), z, slot);
     };
-    // pass 1: speculate (thread l starts one subsequence early, at an assumed block start)
+    // pass 1: speculate (thread l starts `warm` subsequences early, at an assumed block start)
     for (uint32_t l = 0; l < nsub; l++) {
         uint64_t st;
         if (l == 0) st = pack_state(b0, z0, 0);
         else {
-            uint64_t own = b0 + (uint64_t)l * S;
+            uint32_t own = l * (uint32_t)S;
             BitReader<HostSrc> rd;
-            rd.seek(&src, own - S * (uint64_t)((uint32_t)warm < l ? (uint32_t)warm : l));
+            rd.seek(&src, b0, own - (uint32_t)S * ((uint32_t)warm < l ? (uint32_t)warm : l));
             int z = z0, slot = 0;
             SubCount k{0, {0, 0, 0}};
-            if (sc.mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, c, ~0ull, own, b1, k);
-            else if (sc.mode == BJ_MODE_DC_FIRST) sync_run<BJ_M_DCFIRST>(rd, z, slot, c, ~0ull, own, b1, k);
+            if (sc.mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, c, sc.lut, 0xFFFFFFFFu, own, nbits, k);
+            else if (sc.mode == BJ_MODE_DC_FIRST) sync_run<BJ_M_DCFIRST>(rd, z, slot, c, sc.lut, 0xFFFFFFFFu, own, nbits, k);
             else {
                 uint32_t blk = 0, adv = 0;
-                acfirst_run<false>(rd, z, c, ~0ull, own, b1, blk, 0xFFFFFFFFu, adv, dummy);
+                acfirst_run<false>(rd, z, c, sc.lut, 0xFFFFFFFFu, own, nbits, blk, 0xFFFFFFFFu, adv, dummy);
             }
-            st = pack_state(rd.pos, z, slot);
+            st = pack_state(rd.abs_pos(), z, slot);
         }
         entry[l] = st;
         run_sub(l, st);
@@ -170,20 +170,19 @@ uint32_t hs_decode_stream(const uint32_t* words, uint64_t n_words, uint64_t star
     BlockSink sink{};
     sink.out = coef;
     for (uint32_t l = 0; l < nsub; l++) {
-        uint64_t own = b0 + (uint64_t)l * S, stop = own + S < b1 ? own + S : b1;
+        uint32_t own = l * (uint32_t)S, stop = own + (uint32_t)S < nbits ? own + (uint32_t)S : nbits;
         BitReader<HostSrc> rd;
-        rd.seek(&src, state_pos(entry[l]));
+        rd.seek(&src, b0, (uint32_t)(state_pos(entry[l]) - b0));
         int z = state_z(entry[l]), slot = state_slot(entry[l]);
         uint32_t blk = pre[l].blocks;
         int pred[3] = {pre[l].dc[0], pre[l].dc[1], pre[l].dc[2]};
         if (sc.mode == BJ_MODE_BASELINE) {
-            if (z != 0) { /* the open block belongs to the previous subsequence */ }
-            err |= base_write_run(rd, z, slot, c, stop, b1, blk, nblk_stream, pred, sink);
+            err |= base_write_run(rd, z, slot, c, sc.lut, stop, nbits, blk, nblk_stream, pred, sink);
         } else if (sc.mode == BJ_MODE_DC_FIRST) {
-            err |= dcfirst_write_run(rd, slot, c, stop, b1, blk, nblk_stream, pred, sink);
+            err |= dcfirst_write_run(rd, slot, c, sc.lut, stop, nbits, blk, nblk_stream, pred, sink);
         } else {
             uint32_t adv = 0;
-            err |= acfirst_run<true>(rd, z, c, own, stop, b1, blk, nblk_stream, adv, sink);
+            err |= acfirst_run<true>(rd, z, c, sc.lut, own, stop, nbits, blk, nblk_stream, adv, sink);
         }
     }
     if (acc.blocks < nblk_stream) err |= BJ_ERR_OVERRUN;
@@ -200,9 +199,9 @@ uint32_t hs_acrefine_stream(const uint32_t* words, uint64_t n_words, uint64_t st
     ScanCtx c = make_ctx(*ss_);
     HostSrc src{words, n_words};
     BitReader<HostSrc> rd;
-    rd.seek(&src, start_byte * 8);
+    rd.seek(&src, start_byte * 8, 0);
     HostCoef hc{coef};
-    return acrefine_stream(rd, c, end_byte * 8, nblk_stream, hc);
+    return acrefine_stream(rd, c, ss_->lut, (uint32_t)((end_byte - start_byte) * 8), nblk_stream, hc);
 }
 
 // DC refinement (:1036-1043): bit b of the stream belongs to block b.

@@ -92,6 +92,6 @@ def test_huffman_lut_decodes_every_code():
             for code, length, sym in canonical_codes(spec):
                 peek = (code << (16 - length)) | ((1 << (16 - length)) - 1)   # code followed by ones
                 e = int(t[peek >> 7])
-                if e & 0x80000000:
-                    e = int(t[(e & 0xFFFF) + (peek & 127)])
-                assert (e & 255, (e >> 8) & 31) == (sym, length), (name, dest, code, length)
+                if e & 0x80:
+                    e = int(t[((e >> 8) & 0xFFFF) + (peek & 127)])
+                assert (e >> 24, (e >> 16) & 255) == (sym, length), (name, dest, code, length)
