@@ -71,7 +71,39 @@ struct CtaShared {
     uint32_t lut[1];   // lut_cap entries follow
 };
 
+// The fix-up kernel is latency bound (a few subsequences are re-decoded per round), so it trades the
+// shared-memory copies of the bit window and the LUTs for occupancy: it reads both through L1.
+struct CtaSharedLite {
+    bj_scan sc;
+    ScanCtx ctx;
+    uint32_t scan_nsub;
+};
+
 // ---- helpers -------------------------------------------------------------------------------------
+template <class SH>
+__device__ __forceinline__ void load_scan_header(SH& sh, const bj_scan* scans, int idx, const bj_entropy_buffers& B) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[idx]);
+    for (int i = threadIdx.x; i < (int)(sizeof(bj_scan) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&sh.sc)[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bj_scan& sc = sh.sc;
+        for (int i = 0; i < BJ_MAX_SLOTS; i++) {
+            sh.ctx.dc_tab[i] = sc.slot_dc[i];
+            sh.ctx.ac_tab[i] = sc.slot_ac[i];
+            sh.ctx.slot_comp[i] = sc.slot_comp[i];
+        }
+        sh.ctx.nslots = sc.nslots;
+        sh.ctx.ss = sc.ss;
+        sh.ctx.se = sc.se;
+        sh.ctx.al = sc.al;
+        // total subsequences of the scan = first subsequence of the last stream + its own count
+        uint32_t last = sc.stream0 + sc.n_streams - 1;
+        uint64_t bits = (B.stream_end[last] - B.stream_start[last]) * 8;
+        sh.scan_nsub = B.stream_sub[last] + (uint32_t)((bits + S - 1) / S);
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void load_scan(CtaShared& sh, const bj_scan* scans, int idx, const bj_entropy_buffers& B,
                                           uint32_t lut_cap) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[idx]);
@@ -111,7 +143,8 @@ struct SubInfo {
     uint32_t mcu0;       // first MCU of the stream
 };
 
-__device__ __forceinline__ SubInfo locate(const CtaShared& sh, const bj_entropy_buffers& B, uint32_t lscan) {
+template <class SH>
+__device__ __forceinline__ SubInfo locate(const SH& sh, const bj_entropy_buffers& B, uint32_t lscan) {
     SubInfo s;
     const bj_scan& sc = sh.sc;
     s.valid = lscan < sh.scan_nsub;
@@ -158,25 +191,23 @@ __device__ __forceinline__ WinSrc win_src(const CtaShared& sh, const bj_entropy_
     return WinSrc{sh.win, sh.win_w0, sh.win_n, B.words, (uint32_t)B.words_len};
 }
 
-// Decode subsequence `si` from entry state st: exit state + counts.  LUT_SMEM selects the shared-memory
-// copy of the scan's tables (compiles to LDS) or, for oversized tables, the global copy.
-template <bool LUT_SMEM, class Src>
-__device__ __forceinline__ void run_sub_impl(const CtaShared& sh, const uint32_t* __restrict__ glut, const Src& src,
-                                             uint64_t b0, uint32_t own_rel, uint32_t stop_rel, uint32_t end_rel, uint64_t st,
-                                             uint64_t& ex, SubCount& k) {
-    const uint32_t* lut = LUT_SMEM ? sh.lut : glut;
+// Decode one subsequence from entry state st: exit state + counts.  `lut` must be passed with visible
+// provenance (sh.lut -> LDS, or a global pointer).
+template <class Src>
+__device__ __forceinline__ void run_sub_core(int mode, const ScanCtx& ctx, const uint32_t* lut, const Src& src, uint64_t b0,
+                                             uint32_t own_rel, uint32_t stop_rel, uint32_t end_rel, uint64_t st, uint64_t& ex,
+                                             SubCount& k) {
     BitReader<Src> rd;
     rd.seek(&src, b0, (uint32_t)(state_pos(st) - b0));
     int z = state_z(st), slot = state_slot(st);
     k.blocks = 0;
     k.dc[0] = k.dc[1] = k.dc[2] = 0;
-    const int mode = sh.sc.mode;
-    if (mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, sh.ctx, lut, own_rel, stop_rel, end_rel, k);
-    else if (mode == BJ_MODE_DC_FIRST) sync_run<BJ_M_DCFIRST>(rd, z, slot, sh.ctx, lut, own_rel, stop_rel, end_rel, k);
+    if (mode == BJ_MODE_BASELINE) sync_run<BJ_M_BASE>(rd, z, slot, ctx, lut, own_rel, stop_rel, end_rel, k);
+    else if (mode == BJ_MODE_DC_FIRST) sync_run<BJ_M_DCFIRST>(rd, z, slot, ctx, lut, own_rel, stop_rel, end_rel, k);
     else {
         struct NoSink { __device__ void store(uint32_t, int, int16_t) {} } ns;
         uint32_t blk = 0, adv = 0;
-        acfirst_run<false>(rd, z, sh.ctx, lut, own_rel, stop_rel, end_rel, blk, 0xFFFFFFFFu, adv, ns);
+        acfirst_run<false>(rd, z, ctx, lut, own_rel, stop_rel, end_rel, blk, 0xFFFFFFFFu, adv, ns);
         k.blocks = adv;
     }
     ex = pack_state(rd.abs_pos(), z, slot);
@@ -186,8 +217,8 @@ template <class Src>
 __device__ __forceinline__ void run_sub(const CtaShared& sh, const bj_entropy_buffers& B, const Src& src, uint64_t b0,
                                         uint32_t own_rel, uint32_t stop_rel, uint32_t end_rel, uint64_t st, uint64_t& ex,
                                         SubCount& k) {
-    if (sh.lut_in_smem) run_sub_impl<true>(sh, nullptr, src, b0, own_rel, stop_rel, end_rel, st, ex, k);
-    else run_sub_impl<false>(sh, B.lut + sh.sc.lut_off, src, b0, own_rel, stop_rel, end_rel, st, ex, k);
+    if (sh.lut_in_smem) run_sub_core(sh.sc.mode, sh.ctx, sh.lut, src, b0, own_rel, stop_rel, end_rel, st, ex, k);
+    else run_sub_core(sh.sc.mode, sh.ctx, B.lut + sh.sc.lut_off, src, b0, own_rel, stop_rel, end_rel, st, ex, k);
 }
 
 // ---- plan ------------------------------------------------------------------------------------------
@@ -277,9 +308,8 @@ __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ sca
 // into a dense list and decoded by the first threads of the CTA, so that warps stay full even when
 // only a few subsequences per round need work.
 __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
-                                                uint32_t* __restrict__ chain, uint32_t lut_cap) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
+                                                uint32_t* __restrict__ chain) {
+    __shared__ CtaSharedLite sh;
     __shared__ uint64_t s_entry[T], s_exit[T];
     __shared__ uint64_t s_b0[T];
     __shared__ uint32_t s_ownr[T], s_stopr[T], s_endr[T];
@@ -290,17 +320,14 @@ __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scan
     __shared__ uint32_t s_tail[T / 32][4];
     __shared__ uint64_t s_prev_exit;
     __shared__ uint32_t s_carry[4];
-    __shared__ uint64_t first_bit;
-    load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
+    load_scan_header(sh, scans, scan_first + blockIdx.x, B);
     const uint32_t base = blockIdx.y * T;
     if (base >= sh.scan_nsub) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lscan = base + tid;
     SubInfo si = locate(sh, B, lscan);
-    if (tid == 0) first_bit = si.own;
-    __syncthreads();
-    load_window(sh, B, first_bit);
-    WinSrc src = win_src(sh, B);
+    GlobalSrc src{B.words, (uint32_t)B.words_len};
+    const uint32_t* const glut = B.lut + sh.sc.lut_off;
     const size_t g = (size_t)sh.sc.sub0 + lscan;
     {
         uint64_t entry = 0, ex = 0;
@@ -354,7 +381,7 @@ __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scan
                 const int j = s_list[tid];
                 uint64_t ex;
                 SubCount k;
-                run_sub(sh, B, src, s_b0[j], s_ownr[j], s_stopr[j], s_endr[j], s_entry[j], ex, k);
+                run_sub_core(sh.sc.mode, sh.ctx, glut, src, s_b0[j], s_ownr[j], s_stopr[j], s_endr[j], s_entry[j], ex, k);
                 s_exit[j] = ex;
                 s_cnt[j][0] = k.blocks; s_cnt[j][1] = (uint32_t)k.dc[0]; s_cnt[j][2] = (uint32_t)k.dc[1]; s_cnt[j][3] = (uint32_t)k.dc[2];
                 changes++;
@@ -626,7 +653,6 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
     if (mode == BJ_MODE_BASELINE || mode == BJ_MODE_DC_FIRST || mode == BJ_MODE_AC_FIRST) {
         if (!chain || max_sub == 0) return BJ_E_ARG;
         e = cudaFuncSetAttribute(spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
         dim3 grid((unsigned)n_scans, (max_sub + T - 1) / T);
@@ -635,7 +661,7 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         if (phases & BJ_PHASE_FIX) {
             e = cudaMemsetAsync(chain, 0, sizeof(uint32_t) * kChainWords * (size_t)grid.x * grid.y, st);
             if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/memset");
-            fix_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, chain, lut_cap);
+            fix_kernel<<<grid, T, 0, st>>>(scans, scan_first, *bufs, chain);
         }
         if (phases & BJ_PHASE_WRITE) write_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
     } else if (mode == BJ_MODE_DC_REFINE) {
