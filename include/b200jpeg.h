@@ -75,7 +75,8 @@ typedef struct bj_image {
     uint8_t hmax, vmax;
     uint8_t blocks_per_mcu;
     uint8_t slot0[BJ_MAX_COMP];   /* first block slot of each component inside an MCU */
-    uint16_t strip_mcus;          /* MCUs handled by one CTA of the pixel kernels (host-chosen, <= 192 / blocks_per_mcu) */
+    uint16_t strip_mcus;          /* MCUs handled by one CTA of the pixel kernels: bj_pixels_fast_strip(layout) for the
+                                     specialised layouts, else host-chosen <= 192 / blocks_per_mcu */
     uint16_t strips_per_row;      /* ceil(mcus_x / strip_mcus) */
     uint32_t layout;              /* BJ_LAYOUT_*: selects the specialised pixel kernel (0 = generic) */
 } bj_image;
@@ -219,6 +220,7 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
 int bj_version(void);
 int bj_sizeof(int what);         /* 0: sizeof(bj_image) -- lets a binding verify its struct mirrors */
 int bj_sizeof_entropy(int what); /* 1: sizeof(bj_scan), 2: sizeof(bj_entropy_buffers) */
+int bj_pixels_fast_strip(int layout); /* MCUs per CTA the specialised pixel kernel uses for BJ_LAYOUT_* (0: generic) */
 const char* bj_last_cuda_error(void);
 
 /*

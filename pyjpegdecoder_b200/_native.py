@@ -55,6 +55,12 @@ def lib():
                             ctypes.c_uint32, c_void_p, c_void_p]
     if L.bj_sizeof(0) != IMAGE_DTYPE.itemsize:
         raise NativeLibraryError("struct bj_image layout mismatch between Python and libb200jpeg.so")
+    L.bj_pixels_fast_strip.restype = c_int
+    L.bj_pixels_fast_strip.argtypes = [c_int]
+    from .plan import FAST_STRIP
+    for lay, strip in FAST_STRIP.items():
+        if L.bj_pixels_fast_strip(lay) != strip:
+            raise NativeLibraryError("pixel-kernel strip sizes differ between Python and libb200jpeg.so")
     _LIB = L
     return L
 

@@ -4,14 +4,20 @@
 // Same arithmetic contract as the generic kernel in bj_pixels.cu (bit-exact with the reference's
 // fp64 path, jpeg_decoder.py:869-891, :1306-1366, :1368-1386, :1683-1700) but the sampling layout is
 // a template parameter (4:2:0, 4:2:2, 4:4:0, 4:4:4, greyscale), so every index computation, division
-// and branch on the geometry folds at compile time.  What changes versus the generic kernel:
+// and branch on the geometry folds at compile time.
+//
+// WARP-AUTONOMOUS design: a warp owns 32/blocks_per_mcu whole MCUs (4:2:0: 5 MCUs = 30 blocks) and
+// does everything for them -- cp.async load of its contiguous 128-byte coefficient blocks into its
+// private, bank-swizzled shared-memory tile, one lane per block for the register IDCT, the exact
+// recompute of flagged blocks, the per-pixel colour stage and the stores of its 16-row output
+// segment -- with __syncwarp() only.  After the one-time table set-up there is no CTA barrier, so the
+// 18 warps of an SM run at independent phases and hide each other's load/store latency.
 //   * luma samples stay int16 in shared memory (128 B per block); only chroma is kept as fp32
 //     because it is interpolated.  R/G/B = clamp(Y + round(offset(Cb,Cr))): the rounding tie test
 //     only involves the chroma offsets (Y is an integer), see bj_pixel_math.cuh;
 //   * add + clamp is one VIADDMNMX (__viaddmin_s32_relu);
 //   * the exact fp64 recompute of a flagged block iterates over its non-zero coefficients only
-//     (ballot masks), in numpy's pairwise order;
-//   * 60 KB of shared memory per CTA -> 3 CTAs (18 warps) per SM.
+//     (ballot masks), in numpy's pairwise order.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,9 +28,9 @@ extern "C" bj_status bj_set_cuda_error(cudaError_t e, const char* where);
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr int kWarps = kThreads / 32;
-constexpr int kTileABytes = 192 * 128 + 512;
+constexpr int kWarps = 6;
+constexpr int kThreads = kWarps * 32;
+constexpr int kWStride = 17;  // float4 entries per weight-table row (16 + 1 pad: lanes read different rows)
 
 template <int HMAX_, int VMAX_, int NCOMP_>
 struct Lay {
@@ -33,26 +39,38 @@ struct Lay {
     static constexpr int BPM = NY + (NCOMP == 3 ? 2 : 0);
     static constexpr int MCU_W = 8 * HMAX, MCU_H = 8 * VMAX;
     static constexpr bool UPS = (NCOMP == 3) && (NY > 1);
-    static constexpr int MAXM = 192 / BPM;
-    static constexpr int MCU_B = NY * 128 + (NCOMP == 3 ? 512 : 0);  // tile B bytes per MCU
     static constexpr int CH = NCOMP == 3 ? 3 : 1;
-    static constexpr int TILE_B = MAXM * MCU_B;
-    static constexpr int W_BYTES = UPS ? 256 * 16 : 0;
-    static constexpr int SMEM = kTileABytes + TILE_B + W_BYTES + 3 * 128 + 64 + 64;
+    static constexpr int MPW = 32 / BPM;          // MCUs per warp
+    static constexpr int STRIP = kWarps * MPW;    // MCUs per CTA (must match plan.py: choose_strip)
+    static constexpr int MCU_B = NY * 128 + (NCOMP == 3 ? 512 : 0);  // sample-tile bytes per MCU
+    static constexpr int A_BYTES = 32 * 128;      // coefficient tile of a warp, reused as RGB staging
+    static constexpr int B_BYTES = MPW * MCU_B;
+    static constexpr int WARP_BYTES = A_BYTES + B_BYTES;
+    static constexpr int ROW_BYTES = MPW * MCU_W * CH;  // one staged output row of a warp
+    static constexpr int W_BYTES = UPS ? 16 * kWStride * 16 : 0;
+    static constexpr int SMEM = kWarps * WARP_BYTES + W_BYTES + 3 * 128;
+    static_assert(ROW_BYTES % 16 == 0 && ROW_BYTES * MCU_H <= A_BYTES, "staging must fit the coefficient tile");
 };
 
-__constant__ uint8_t c_zz_nat2[64] = {BJ_ZZ_NATURAL};
+// reference flat index u*8+v -> zig-zag index (zagzig, jpeg_decoder.py:1672-1681, inverted)
+__constant__ uint8_t c_nat_zz[64] = {0, 2, 3, 9, 10, 20, 21, 35, 1, 4, 8, 11, 19, 22, 34, 36, 5, 7, 12, 18, 23, 33,
+                                     37, 48, 6, 13, 17, 24, 32, 38, 47, 49, 14, 16, 25, 31, 39, 46, 50, 57, 15, 26,
+                                     30, 40, 45, 51, 56, 58, 27, 29, 41, 44, 52, 55, 59, 62, 28, 42, 43, 53, 54, 60,
+                                     61, 63};
 
-__device__ __forceinline__ int swzA(int blk, int chunk) { return blk * 128 + ((chunk ^ (blk & 7)) << 4); }
-__device__ __forceinline__ float int_to_float_magic(int v) { return __int_as_float(v + BJ_MAGIC_BITS) - BJ_MAGIC; }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 template <class L>
 struct Tiles {
-    unsigned char* a;   // coefficients / RGB staging
-    unsigned char* b;   // samples
-    float4* w;          // interpolation weights [b*16 + a]
-    int16_t* qt;        // [3][64]
-    uint8_t* nat_zz;    // u*8+v -> zig-zag index
+    unsigned char* a;   // this warp's coefficients (32 x 128 B, swizzled) / RGB staging
+    unsigned char* b;   // this warp's samples
+    const float4* w;    // interpolation weights [b * kWStride + a]
+    const int16_t* qt;  // [3][64]
+    __device__ __forceinline__ unsigned char* coef_chunk(int blk, int c) const { return a + blk * 128 + ((c ^ (blk & 7)) << 4); }
     // luma block ys of MCU m, row y: 8 int16
     __device__ __forceinline__ unsigned char* yrow(int m, int ys, int y) const {
         return b + m * L::MCU_B + ys * 128 + ((y ^ ((m + ys) & 7)) << 4);
@@ -68,13 +86,14 @@ struct Tiles {
 // of u = 0..7 in order, then ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)): numpy's pairwise sum of the 64
 // products in C order [u][v]; zero coefficients only add +-0.0 and are skipped.
 template <class L>
-__device__ void recompute_block_exact(const Tiles<L>& t, int blk, int m, int slot, const double* __restrict__ tabT, int lane) {
+__device__ __noinline__ void recompute_block_exact(const Tiles<L>& t, int blk, const double* __restrict__ tabT, int lane) {
+    const int m = blk / L::BPM, slot = blk - m * L::BPM;
     const int comp = slot < L::NY ? 0 : slot - L::NY + 1;
     const int16_t* qt = t.qt + comp * 64;
     // natural-order non-zero masks: lane l looks at n = l and n = l + 32
-    int k0 = t.nat_zz[lane], k1 = t.nat_zz[lane + 32];
-    int c0 = *reinterpret_cast<const int16_t*>(t.a + swzA(blk, k0 >> 3) + ((k0 & 7) << 1));
-    int c1 = *reinterpret_cast<const int16_t*>(t.a + swzA(blk, k1 >> 3) + ((k1 & 7) << 1));
+    int k0 = c_nat_zz[lane], k1 = c_nat_zz[lane + 32];
+    int c0 = *reinterpret_cast<const int16_t*>(t.coef_chunk(blk, k0 >> 3) + ((k0 & 7) << 1));
+    int c1 = *reinterpret_cast<const int16_t*>(t.coef_chunk(blk, k1 >> 3) + ((k1 & 7) << 1));
     int p0 = (int16_t)(c0 * (int)qt[k0]), p1 = (int16_t)(c1 * (int)qt[k1]);  // int16 product wraps (:869)
     const unsigned nz_lo = __ballot_sync(0xffffffffu, p0 != 0), nz_hi = __ballot_sync(0xffffffffu, p1 != 0);
     double r0[8], r1[8];
@@ -125,16 +144,16 @@ __device__ __noinline__ uint32_t ycc_to_rgb_exact_packed(int Yi, float Cbf, floa
 
 template <int A> struct Cell { static constexpr int i = (A == 15) ? 6 : (7 * A) / 15; };
 
+// One 8-pixel run: pixel row r (0..MCU_H-1) of MCU m (warp-local), horizontal half HX.
 template <class L, int HX>
-__device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int row_stride_s, uint32_t* stats) {
-    // luma: 8 int16 of row r
+__device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, uint32_t* stats) {
     const int ys = (r >> 3) * L::HMAX + HX, yy = r & 7;
     const uint4 yv = *reinterpret_cast<const uint4*>(t.yrow(m, ys, yy));
     const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
     int Y[8];
 #pragma unroll
     for (int p = 0; p < 8; p++) Y[p] = (int)(int16_t)(yw[p >> 1] >> (16 * (p & 1)));
-    const int px0 = m * L::MCU_W + 8 * HX;
+    unsigned char* stage = t.a + r * L::ROW_BYTES + (m * L::MCU_W + 8 * HX) * L::CH;
     if (L::NCOMP == 1) {
         uint32_t lo = 0, hi = 0;
 #pragma unroll
@@ -142,22 +161,27 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int r
             lo |= (uint32_t)min(max(Y[p], 0), 255) << (8 * p);  // (:1385-1386)
             hi |= (uint32_t)min(max(Y[p + 4], 0), 255) << (8 * p);
         }
-        *reinterpret_cast<uint2*>(t.a + r * row_stride_s + px0) = make_uint2(lo, hi);
+        *reinterpret_cast<uint2*>(stage) = make_uint2(lo, hi);
         return;
     }
-    float cb[8], cr[8];
+    // chroma minus 128 for the 8 pixels
+    float cbm[8], crm[8];
     if (!L::UPS) {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             float4 lo = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * yy));
             float4 hi = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * yy + 1));
-            float* o = k ? cr : cb;
-            o[0] = lo.x; o[1] = lo.y; o[2] = lo.z; o[3] = lo.w; o[4] = hi.x; o[5] = hi.y; o[6] = hi.z; o[7] = hi.w;
+            float* o = k ? crm : cbm;
+            o[0] = lo.x - 128.f; o[1] = lo.y - 128.f; o[2] = lo.z - 128.f; o[3] = lo.w - 128.f;
+            o[4] = hi.x - 128.f; o[5] = hi.y - 128.f; o[6] = hi.z - 128.f; o[7] = hi.w - 128.f;
         }
     } else {
         int j = (L::VMAX == 2) ? ((r == 15) ? 6 : (7 * r) / 15) : r;
         int j2 = j < 7 ? j + 1 : 7;
-        const float4* w = t.w + r * 16 + 8 * HX;
+        const float4* w = t.w + r * kWStride + 8 * HX;
+        float4 ww[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) ww[p] = w[p];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             float p0[8], p1[8];
@@ -169,14 +193,14 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int r
                 p0[0] = a0.x; p0[1] = a0.y; p0[2] = a0.z; p0[3] = a0.w; p0[4] = a1.x; p0[5] = a1.y; p0[6] = a1.z; p0[7] = a1.w;
                 p1[0] = b0.x; p1[1] = b0.y; p1[2] = b0.z; p1[3] = b0.w; p1[4] = b1.x; p1[5] = b1.y; p1[6] = b1.z; p1[7] = b1.w;
             }
-            float* o = k ? cr : cb;
-#define BJ_PIX(P)                                                                          \
-    {                                                                                      \
-        constexpr int i = (L::HMAX == 2) ? Cell<8 * HX + P>::i : P;                        \
-        constexpr int i2 = i < 7 ? i + 1 : 7;                                              \
-        float4 ww = w[P];                                                                  \
-        float n = fmaf(ww.w, p1[i2], fmaf(ww.z, p1[i], fmaf(ww.y, p0[i2], ww.x * p0[i]))); \
-        o[P] = bj::div15_round(n);                                                         \
+            float* o = k ? crm : cbm;
+#define BJ_PIX(P)                                                                                          \
+    {                                                                                                      \
+        constexpr int i = (L::HMAX == 2) ? Cell<8 * HX + P>::i : P;                                        \
+        constexpr int i2 = i < 7 ? i + 1 : 7;                                                              \
+        float n = fmaf(ww[P].w, p1[i2], fmaf(ww[P].z, p1[i], fmaf(ww[P].y, p0[i2], ww[P].x * p0[i])));     \
+        /* N/15 rounded (never a tie), minus 128: both subtractions folded into one exact fp32 add */      \
+        o[P] = fmaf(n, 1.0f / 15.0f, BJ_MAGIC) - (BJ_MAGIC + 128.0f);                                      \
     }
             BJ_PIX(0) BJ_PIX(1) BJ_PIX(2) BJ_PIX(3) BJ_PIX(4) BJ_PIX(5) BJ_PIX(6) BJ_PIX(7)
 #undef BJ_PIX
@@ -188,12 +212,12 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int r
     bool btie = false;
 #pragma unroll
     for (int p = 0; p < 8; p++) {
-        float cbm = cb[p] - 128.0f, crm = cr[p] - 128.0f;
-        float rC = 1.402f * crm, gC = fmaf(-0.71414f, crm, -0.34414f * cbm), bC = 1.772f * cbm;
+        const float cb = cbm[p], cr = crm[p];
+        float rC = 1.402f * cr, gC = fmaf(-0.71414f, cr, -0.34414f * cb), bC = 1.772f * cb;
         float wr = rC + BJ_MAGIC, wg = gC + BJ_MAGIC, wb = bC + BJ_MAGIC;
         dgmax = fmaxf(dgmax, fabsf(gC - (wg - BJ_MAGIC)));
-        guard = fmaxf(guard, fmaxf(fabsf(cbm), fabsf(crm)));
-        btie = btie || (fabsf(cbm) == 125.0f);
+        guard = fmaxf(guard, fmaxf(fabsf(cb), fabsf(cr)));
+        btie = btie || (fabsf(cb) == 125.0f);
         const int yb = Y[p] - BJ_MAGIC_BITS;
         uint32_t R = (uint32_t)__viaddmin_s32_relu(__float_as_int(wr), yb, 255);
         uint32_t G = (uint32_t)__viaddmin_s32_relu(__float_as_int(wg), yb, 255);
@@ -202,7 +226,7 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int r
     }
     if (btie || guard >= BJ_CHROMA_GUARD || dgmax > 0.5f - BJ_G_ERR) {
 #pragma unroll 1
-        for (int p = 0; p < 8; p++) rgb[p] = ycc_to_rgb_exact_packed(Y[p], cb[p], cr[p]);
+        for (int p = 0; p < 8; p++) rgb[p] = ycc_to_rgb_exact_packed(Y[p], cbm[p] + 128.0f, crm[p] + 128.0f);
         if (stats) atomicAdd(&stats[1], 8u);
     }
     // 8 pixels x 3 bytes = 6 words
@@ -213,7 +237,7 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int r
     o[3] = rgb[4] | (rgb[5] << 24);
     o[4] = (rgb[5] >> 8) | (rgb[6] << 16);
     o[5] = (rgb[6] >> 16) | (rgb[7] << 8);
-    uint2* s2 = reinterpret_cast<uint2*>(t.a + r * row_stride_s + px0 * 3);
+    uint2* s2 = reinterpret_cast<uint2*>(stage);
     s2[0] = make_uint2(o[0], o[1]);
     s2[1] = make_uint2(o[2], o[3]);
     s2[2] = make_uint2(o[4], o[5]);
@@ -234,27 +258,13 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
     }
     __syncthreads();
     if ((int)im.layout != LAYOUT) return;
-    const int strips_total = im.mcus_y * im.strips_per_row;
-    if ((int)blockIdx.x >= strips_total) return;
-    Tiles<L> t;
-    t.a = smem;
-    t.b = smem + kTileABytes;
-    t.w = reinterpret_cast<float4*>(t.b + L::TILE_B);
-    t.qt = reinterpret_cast<int16_t*>(reinterpret_cast<unsigned char*>(t.w) + L::W_BYTES);
-    t.nat_zz = reinterpret_cast<uint8_t*>(t.qt + 3 * 64);
+    const int strips_per_row = ((int)im.mcus_x + L::STRIP - 1) / L::STRIP;
+    if ((int)blockIdx.x >= (int)im.mcus_y * strips_per_row) return;
 
-    const int my = blockIdx.x / im.strips_per_row;
-    const int m0 = (blockIdx.x % im.strips_per_row) * im.strip_mcus;
-    const int M = min(min((int)im.strip_mcus, (int)im.mcus_x - m0), L::MAXM);
-    const int nblk = M * L::BPM;
-    const int64_t gblk0 = (int64_t)im.coef_block0 + ((int64_t)my * im.mcus_x + m0) * L::BPM;
-
-    // ---- tables + coefficient load ----------------------------------------------------------------
-    if (tid < 64) {
-        int nat = c_zz_nat2[tid];
-        t.nat_zz[(nat & 7) * 8 + (nat >> 3)] = (uint8_t)tid;
-    }
-    for (int i = tid; i < NCOMP * 64; i += kThreads) t.qt[i] = qtabs[(size_t)im.qtab[i >> 6] * 64 + (i & 63)];
+    // ---- CTA-wide tables (the only CTA barrier of the kernel) ---------------------------------------
+    float4* wtab = reinterpret_cast<float4*>(smem + kWarps * L::WARP_BYTES);
+    int16_t* qt = reinterpret_cast<int16_t*>(smem + kWarps * L::WARP_BYTES + L::W_BYTES);
+    for (int i = tid; i < NCOMP * 64; i += kThreads) qt[i] = qtabs[(size_t)im.qtab[i >> 6] * 64 + (i & 63)];
     if (L::UPS) {
         for (int i = tid; i < 256; i += kThreads) {
             int b = i >> 4, a = i & 15;
@@ -263,18 +273,34 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
             if (VMAX == 2) bj::up_cell(b, jj, tt);
             int w00, w10, w01, w11;
             bj::up_weights_2d(ii, jj, s, tt, w00, w10, w01, w11);
-            t.w[i] = make_float4((float)w00, (float)w10, (float)w01, (float)w11);
+            wtab[b * kWStride + a] = make_float4((float)w00, (float)w10, (float)w01, (float)w11);
         }
     }
-    {
-        const uint4* g = reinterpret_cast<const uint4*>(coef + gblk0 * 64);
-        for (int i = tid; i < nblk * 8; i += kThreads) *reinterpret_cast<uint4*>(t.a + swzA(i >> 3, i & 7)) = __ldg(g + i);
+    // ---- this warp's tile ----------------------------------------------------------------------------
+    const int my = blockIdx.x / strips_per_row;
+    const int m0 = (blockIdx.x - my * strips_per_row) * L::STRIP + warp * L::MPW;
+    const int M = min(L::MPW, (int)im.mcus_x - m0);
+    Tiles<L> t;
+    t.a = smem + warp * L::WARP_BYTES;
+    t.b = t.a + L::A_BYTES;
+    t.w = wtab;
+    t.qt = qt;
+    const int nblk = M > 0 ? M * L::BPM : 0;
+    if (M > 0) {
+        const uint4* g = reinterpret_cast<const uint4*>(coef + ((int64_t)im.coef_block0 + ((int64_t)my * im.mcus_x + m0) * L::BPM) * 64);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int i = lane + 32 * k;  // 16-byte chunk index inside the warp's tile
+            if (i < nblk * 8) cp_async16(t.coef_chunk(i >> 3, i & 7), g + i);
+        }
     }
+    cp_async_wait_all();
     __syncthreads();
+    if (M <= 0) return;
 
-    // ---- phase A: one thread per block --------------------------------------------------------------
+    // ---- phase A: one lane per block ---------------------------------------------------------------
     {
-        const int blk = tid;
+        const int blk = lane;
         const int m = blk / L::BPM, slot = blk - m * L::BPM;
         bool flagged = false;
         if (blk < nblk) {
@@ -283,15 +309,14 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
             float S = 0.f;
 #pragma unroll
             for (int c = 0; c < 8; c++) {
-                uint4 v = *reinterpret_cast<const uint4*>(t.a + swzA(blk, c));
+                uint4 v = *reinterpret_cast<const uint4*>(t.coef_chunk(blk, c));
                 uint4 q = *reinterpret_cast<const uint4*>(t.qt + comp * 64 + c * 8);
                 const uint32_t vw[4] = {v.x, v.y, v.z, v.w}, qw[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
                     int cf = (int16_t)(vw[e >> 1] >> (16 * (e & 1)));
                     int qq = (int16_t)(qw[e >> 1] >> (16 * (e & 1)));
-                    int prod = (int16_t)(cf * qq);  // int16 * int16 -> int16 wraps (:869, :1348)
-                    float x = int_to_float_magic(prod);
+                    float x = (float)(int16_t)(cf * qq);  // int16 * int16 -> int16 wraps (:869, :1348)
                     constexpr uint8_t zz[64] = {BJ_ZZ_NATURAL};
                     f[zz[c * 8 + e]] = x;
                     if (c * 8 + e) S += fabsf(x);
@@ -300,93 +325,83 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
             const float T = fmaf(S, BJ_IDCT_ERR_REL, fmaf(fabsf(f[0]), BJ_IDCT_ERR_DC, BJ_IDCT_ERR_ABS));
             bj::idct8x8_fast(f);
             float maxd = 0.f;
-            if (comp == 0) {
 #pragma unroll
-                for (int y = 0; y < 8; y++) {
-                    uint32_t wv[8];
+            for (int y = 0; y < 8; y++) {
+                float w[8];
 #pragma unroll
-                    for (int x = 0; x < 8; x++) {
-                        float v = f[y * 8 + x];
-                        float w = v + BJ_MAGIC;
-                        maxd = fmaxf(maxd, fabsf(v - (w - BJ_MAGIC)));
-                        wv[x] = (uint32_t)(__float_as_int(w) - BJ_MAGIC_BITS + 128);
-                    }
-                    uint4 o = make_uint4(__byte_perm(wv[0], wv[1], 0x5410), __byte_perm(wv[2], wv[3], 0x5410),
-                                         __byte_perm(wv[4], wv[5], 0x5410), __byte_perm(wv[6], wv[7], 0x5410));
-                    *reinterpret_cast<uint4*>(t.yrow(m, slot, y)) = o;
+                for (int x = 0; x < 8; x++) {
+                    float v = f[y * 8 + x];
+                    w[x] = v + BJ_MAGIC;
+                    maxd = fmaxf(maxd, fabsf(v - (w[x] - BJ_MAGIC)));
                 }
-            } else {
+                if (comp == 0) {
+                    uint32_t iv[8];
 #pragma unroll
-                for (int y = 0; y < 8; y++) {
-                    float o[8];
-#pragma unroll
-                    for (int x = 0; x < 8; x++) {
-                        float v = f[y * 8 + x];
-                        float r = (v + BJ_MAGIC) - BJ_MAGIC;
-                        maxd = fmaxf(maxd, fabsf(v - r));
-                        o[x] = r + 128.0f;
-                    }
-                    *reinterpret_cast<float4*>(t.cchunk(m, comp - 1, 2 * y)) = make_float4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<float4*>(t.cchunk(m, comp - 1, 2 * y + 1)) = make_float4(o[4], o[5], o[6], o[7]);
+                    for (int x = 0; x < 8; x++) iv[x] = (uint32_t)(__float_as_int(w[x]) - BJ_MAGIC_BITS + 128);
+                    *reinterpret_cast<uint4*>(t.yrow(m, slot, y)) =
+                        make_uint4(__byte_perm(iv[0], iv[1], 0x5410), __byte_perm(iv[2], iv[3], 0x5410),
+                                   __byte_perm(iv[4], iv[5], 0x5410), __byte_perm(iv[6], iv[7], 0x5410));
+                } else {
+                    // rint(v) + 128 = w - (MAGIC - 128), exact
+                    *reinterpret_cast<float4*>(t.cchunk(m, comp - 1, 2 * y)) =
+                        make_float4(w[0] - (BJ_MAGIC - 128.f), w[1] - (BJ_MAGIC - 128.f), w[2] - (BJ_MAGIC - 128.f), w[3] - (BJ_MAGIC - 128.f));
+                    *reinterpret_cast<float4*>(t.cchunk(m, comp - 1, 2 * y + 1)) =
+                        make_float4(w[4] - (BJ_MAGIC - 128.f), w[5] - (BJ_MAGIC - 128.f), w[6] - (BJ_MAGIC - 128.f), w[7] - (BJ_MAGIC - 128.f));
                 }
             }
             flagged = maxd > 0.5f - T;
         }
         unsigned mask = __ballot_sync(0xffffffffu, flagged);
+        __syncwarp();
         if (mask) {
-            __syncwarp();
             if (stats && lane == 0) atomicAdd(&stats[0], (uint32_t)__popc(mask));
             while (mask) {
                 int src = __ffs(mask) - 1;
                 mask &= mask - 1;
-                int b2 = (warp << 5) + src;
-                int m2 = b2 / L::BPM;
-                recompute_block_exact<L>(t, b2, m2, b2 - m2 * L::BPM, tabT, lane);
+                recompute_block_exact<L>(t, src, tabT, lane);
             }
+            __syncwarp();
         }
     }
-    __syncthreads();
 
-    // ---- phase B: lanes = MCUs, warps walk (pixel row, 8-pixel run) pairs ----------------------------
+    // ---- phase B: lanes = (MCU, pixel row) pairs of this warp -----------------------------------------
     const int x0 = m0 * L::MCU_W, y0 = my * L::MCU_H;
     const int cols = min(M * L::MCU_W, (int)im.width - x0);
     const int rows = min(L::MCU_H, (int)im.height - y0);
-    const int row_stride_s = ((M * L::MCU_W * L::CH) + 15) & ~15;
-    constexpr int pairs = L::MCU_H * L::HMAX;
-    const int chunks = (M + 31) >> 5;
-    for (int it = warp; it < pairs * chunks; it += kWarps) {
-        const int pair = it % pairs, chunk = it / pairs;
-        const int r = pair / L::HMAX, hx = pair % L::HMAX;
-        const int m = (chunk << 5) + lane;
-        if (r >= rows || m >= M) continue;
-        if (L::HMAX == 2 && hx) pixel_run<L, (L::HMAX == 2 ? 1 : 0)>(t, m, r, row_stride_s, stats);
-        else pixel_run<L, 0>(t, m, r, row_stride_s, stats);
+    const int npairs = M * L::MCU_H;
+#pragma unroll 1
+    for (int q0 = 0; q0 < npairs; q0 += 32) {
+        const int q = q0 + lane;
+        const int m = q / L::MCU_H, r = q - m * L::MCU_H;
+        if (q < npairs && r < rows) {
+            pixel_run<L, 0>(t, m, r, stats);
+            if (L::HMAX == 2) pixel_run<L, (L::HMAX == 2 ? 1 : 0)>(t, m, r, stats);
+        }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- coalesced copy-out ----------------------------------------------------------------------------
+    // ---- store this warp's rows -------------------------------------------------------------------------
     uint8_t* gout = out + (int64_t)im.out_offset + (int64_t)y0 * im.out_pitch + (int64_t)x0 * L::CH;
     const int nbytes = cols * L::CH;
     const bool aligned = ((reinterpret_cast<uintptr_t>(gout) & 15) == 0) && ((im.out_pitch & 15) == 0);
-    if (aligned) {
-        const int nvec = nbytes >> 4;
-        for (int i = tid; i < rows * nvec; i += kThreads) {
-            int r = i / nvec, v = i - r * nvec;
-            uint4 val = *reinterpret_cast<const uint4*>(t.a + r * row_stride_s + (v << 4));
+    if (aligned && nbytes == L::ROW_BYTES) {
+        constexpr int NVEC = L::ROW_BYTES / 16;
+        for (int i = lane; i < rows * NVEC; i += 32) {
+            const int r = i / NVEC, v = i - r * NVEC;
+            uint4 val = *reinterpret_cast<const uint4*>(t.a + r * L::ROW_BYTES + (v << 4));
             __stcs(reinterpret_cast<uint4*>(gout + (int64_t)r * im.out_pitch + (v << 4)), val);
         }
-        const int tail = nbytes & 15;
-        if (tail) {
-            for (int i = tid; i < rows * tail; i += kThreads) {
-                int r = i / tail, b = (nvec << 4) + (i - r * tail);
-                gout[(int64_t)r * im.out_pitch + b] = t.a[r * row_stride_s + b];
-            }
+    } else if (aligned) {
+        const int nvec = nbytes >> 4, tail = nbytes & 15;
+        for (int r = 0; r < rows; r++) {
+            for (int v = lane; v < nvec; v += 32)
+                __stcs(reinterpret_cast<uint4*>(gout + (int64_t)r * im.out_pitch + (v << 4)),
+                       *reinterpret_cast<const uint4*>(t.a + r * L::ROW_BYTES + (v << 4)));
+            if (lane < tail) gout[(int64_t)r * im.out_pitch + (nvec << 4) + lane] = t.a[r * L::ROW_BYTES + (nvec << 4) + lane];
         }
     } else {
-        for (int i = tid; i < rows * nbytes; i += kThreads) {
-            int r = i / nbytes, b = i - r * nbytes;
-            gout[(int64_t)r * im.out_pitch + b] = t.a[r * row_stride_s + b];
-        }
+        for (int r = 0; r < rows; r++)
+            for (int b = lane; b < nbytes; b += 32) gout[(int64_t)r * im.out_pitch + b] = t.a[r * L::ROW_BYTES + b];
     }
 }
 
@@ -402,6 +417,19 @@ cudaError_t launch(const bj_image* images, int n_images, int max_strips, const i
 }
 
 }  // namespace
+
+// MCUs per CTA of the specialised kernel for a layout (0 for the generic layout); the host sizes the
+// grid with it (strips_per_row = ceil(mcus_x / strip)).
+extern "C" int bj_pixels_fast_strip(int layout) {
+    switch (layout) {
+        case BJ_LAYOUT_420: return Lay<2, 2, 3>::STRIP;
+        case BJ_LAYOUT_422: return Lay<2, 1, 3>::STRIP;
+        case BJ_LAYOUT_440: return Lay<1, 2, 3>::STRIP;
+        case BJ_LAYOUT_444: return Lay<1, 1, 3>::STRIP;
+        case BJ_LAYOUT_GRAY: return Lay<1, 1, 1>::STRIP;
+        default: return 0;
+    }
+}
 
 // Launch the specialised kernels for every layout present in layout_mask (bits BJ_LAYOUT_420..GRAY).
 extern "C" bj_status bj_pixels_fast_launch(const bj_image* images, int n_images, int max_strips, const int16_t* coef,

@@ -42,8 +42,17 @@ def layout_of(p: ParsedJpeg) -> int:
             (1, 1): _native.LAYOUT_444}.get((c0.h, c0.v), _native.LAYOUT_GENERIC)
 
 
-def choose_strip(mcus_x: int, blocks_per_mcu: int) -> int:
-    """MCUs per CTA of the pixel kernel: as equal as possible, at most 192 blocks."""
+# MCUs per CTA of the layout-specialised kernel: 6 warps x (32 // blocks_per_mcu) MCUs
+# (must equal Lay<...>::STRIP in csrc/bj_pixels_fast.cu; checked against bj_pixels_fast_strip() at load)
+FAST_STRIP = {_native.LAYOUT_420: 30, _native.LAYOUT_422: 48, _native.LAYOUT_440: 48, _native.LAYOUT_444: 60,
+              _native.LAYOUT_GRAY: 192}
+
+
+def choose_strip(mcus_x: int, blocks_per_mcu: int, layout: int = 0) -> int:
+    """MCUs per CTA of the pixel kernels: fixed by the specialised kernel for its layouts, otherwise as
+    equal as possible with at most 192 blocks."""
+    if layout in FAST_STRIP:
+        return FAST_STRIP[layout]
     max_m = max(1, _native.PIXEL_MAX_BLOCKS // blocks_per_mcu)
     n_strips = -(-mcus_x // max_m)
     return -(-mcus_x // n_strips)
@@ -90,11 +99,11 @@ class BatchGeometry:
                     qt_index[key] = len(qt_rows)
                     qt_rows.append(p.qtables[c.tq])
                 rec["qtab"][c.order] = qt_index[key]
-            strip = choose_strip(p.mcus_x, p.blocks_per_mcu)
-            rec["strip_mcus"] = strip
-            rec["strips_per_row"] = -(-p.mcus_x // strip)
             rec["layout"] = layout_of(p)
             self.layout_mask |= 1 << int(rec["layout"])
+            strip = choose_strip(p.mcus_x, p.blocks_per_mcu, int(rec["layout"]))
+            rec["strip_mcus"] = strip
+            rec["strips_per_row"] = -(-p.mcus_x // strip)
             max_strips = max(max_strips, int(rec["strips_per_row"]) * p.mcus_y)
             self.block_offsets.append(blk)
             self.out_offsets.append(out)
