@@ -189,7 +189,7 @@ bj_status bj_entropy_plan(const bj_scan* scans, int scan_first, int n_scans, con
  *   max_streams  max over the wave's scans of n_streams         (AC refine)
  *   max_blocks   max over the wave's scans of n_mcu * nslots    (DC refine)
  *   max_lut      max over the wave's scans of lut_len
- *   chain        workspace, uint32[8 * ceil(max_sub / BJ_ENTROPY_THREADS) * n_scans]
+ *   chain        reserved (may be NULL)
  *   phases       BJ_PHASE_ALL, or a subset of the three kernels of the speculative modes so that a
  *                caller can time them separately (they must still run in this order)
  */

@@ -38,8 +38,6 @@ constexpr int S = BJ_SUBSEQ_BITS;
 constexpr int kWinWords = (T + 1) * (S / 32) + 64;  // bit window of one CTA, in 32-bit words
 constexpr int kMaxLutSmem = 12288;                  // most LUT entries ever staged in shared memory (48 KB)
 
-// chain record per CTA (8 x uint32): exit lo, exit hi, blocks, dc0, dc1, dc2, flag, pad
-constexpr int kChainWords = 8;
 
 struct WinSrc {
     const uint32_t* sw;  // shared window, swizzled
@@ -303,23 +301,21 @@ __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ sca
     reinterpret_cast<uint4*>(B.sub_count)[g] = make_uint4(k.blocks, (uint32_t)k.dc[0], (uint32_t)k.dc[1], (uint32_t)k.dc[2]);
 }
 
-// ---- chained fix-up + prefix sums --------------------------------------------------------------------
-// Re-decodes are COMPACTED: in every round the subsequences whose entry state changed are collected
-// into a dense list and decoded by the first threads of the CTA, so that warps stay full even when
-// only a few subsequences per round need work.
-__global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
-                                                uint32_t* __restrict__ chain) {
+// ---- fix-up, stage 1: CTA-local convergence -----------------------------------------------------------
+// Each CTA iterates (shared memory) until every subsequence's entry state equals its predecessor's
+// exit state, taking the speculative entry of its own first subsequence as given.  Re-decodes are
+// COMPACTED: in every round the subsequences whose entry changed are collected into a dense list and
+// decoded by the first threads of the CTA, so warps stay full even when few subsequences need work.
+// The kernel is latency bound, so it reads the bitstream and the LUTs through L1 instead of staging
+// them (7.7 KB of shared memory per CTA -> 16 CTAs per SM).
+__global__ void __launch_bounds__(T) fix_local_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B) {
     __shared__ CtaSharedLite sh;
     __shared__ uint64_t s_entry[T], s_exit[T];
     __shared__ uint64_t s_b0[T];
     __shared__ uint32_t s_ownr[T], s_stopr[T], s_endr[T];
     __shared__ uint32_t s_cnt[T][4];
-    __shared__ uint32_t s_head[T];
     __shared__ uint16_t s_list[T];
     __shared__ uint32_t s_wcount[T / 32];
-    __shared__ uint32_t s_tail[T / 32][4];
-    __shared__ uint64_t s_prev_exit;
-    __shared__ uint32_t s_carry[4];
     load_scan_header(sh, scans, scan_first + blockIdx.x, B);
     const uint32_t base = blockIdx.y * T;
     if (base >= sh.scan_nsub) return;
@@ -342,139 +338,159 @@ __global__ void __launch_bounds__(T) fix_kernel(const bj_scan* __restrict__ scan
         s_cnt[tid][0] = c.x; s_cnt[tid][1] = c.y; s_cnt[tid][2] = c.z; s_cnt[tid][3] = c.w;
         s_b0[tid] = si.b0; s_ownr[tid] = si.own_rel; s_stopr[tid] = si.stop_rel; s_endr[tid] = si.end_rel;
     }
-    const bool head = si.valid && si.l == 0;          // entry state known exactly
-    const bool needs_prev_cta = (tid == 0) && si.valid && !head;
-    // CTAs of one scan are gridDim.x apart in launch order: by the time chunk c of a scan starts, chunk
-    // c-1 (launched a whole grid row earlier) is usually finished, so the chain wait rarely spins.
-    uint32_t* my_chain = chain + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kChainWords;
-    const uint32_t* prev_chain = my_chain - (size_t)gridDim.x * kChainWords;
+    const bool head = si.valid && si.l == 0;  // entry state known exactly
     uint32_t changes = 0;
-    if (tid == 0) s_prev_exit = s_entry[0];
+    bool dirty = false;
     __syncthreads();
-
-    auto converge = [&]() {
-        for (;;) {
-            // who needs a new entry state?
-            bool need = false;
-            uint64_t want = 0;
-            if (si.valid && !head) {
-                want = (tid == 0) ? s_prev_exit : s_exit[tid - 1];
-                need = s_entry[tid] != want;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, need);
-            if (lane == 0) s_wcount[warp] = __popc(bal);
-            __syncthreads();
-            uint32_t off = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < T / 32; w++) {
-                uint32_t cw = s_wcount[w];
-                if (w < warp) off += cw;
-                total += cw;
-            }
-            if (total == 0) break;
-            if (need) {
-                s_entry[tid] = want;
-                s_list[off + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)tid;
-            }
-            __syncthreads();
-            if ((uint32_t)tid < total) {  // dense: item i is decoded by thread i
-                const int j = s_list[tid];
-                uint64_t ex;
-                SubCount k;
-                run_sub_core(sh.sc.mode, sh.ctx, glut, src, s_b0[j], s_ownr[j], s_stopr[j], s_endr[j], s_entry[j], ex, k);
-                s_exit[j] = ex;
-                s_cnt[j][0] = k.blocks; s_cnt[j][1] = (uint32_t)k.dc[0]; s_cnt[j][2] = (uint32_t)k.dc[1]; s_cnt[j][3] = (uint32_t)k.dc[2];
-                changes++;
-            }
-            __syncthreads();
+    for (;;) {
+        bool need = false;
+        uint64_t want = 0;
+        if (si.valid && !head && tid > 0) {  // thread 0's entry stays speculative here (chain_kernel checks it)
+            want = s_exit[tid - 1];
+            need = s_entry[tid] != want;
         }
-    };
-
-    // 1. local convergence with the speculative entry of the CTA's first subsequence
-    converge();
-    // 2. chain: wait for the previous CTA of this scan, repair if its final exit state differs
-    if (tid == 0) {
-        uint32_t carry[4] = {0, 0, 0, 0};
-        if (needs_prev_cta) {
-            volatile const uint32_t* pc = prev_chain;
-            while (pc[6] == 0u) __nanosleep(40);
-            __threadfence();
-            s_prev_exit = (uint64_t)pc[0] | ((uint64_t)pc[1] << 32);
-            carry[0] = pc[2]; carry[1] = pc[3]; carry[2] = pc[4]; carry[3] = pc[5];
-        }
-        for (int i = 0; i < 4; i++) s_carry[i] = carry[i];
-    }
-    __syncthreads();
-    converge();
-    // 3. publish early: exit state of the CTA's last subsequence and the running totals of the stream
-    //    that is open at the CTA's end = counts since the last stream head (+ carry-in if none).
-    const uint32_t last = min((uint32_t)T, sh.scan_nsub - base) - 1;
-    uint32_t own[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) own[i] = si.valid ? s_cnt[tid][i] : 0u;
-    {
-        const unsigned hb = __ballot_sync(0xffffffffu, head);
-        if (lane == 0) s_wcount[warp] = hb;
+        const unsigned bal = __ballot_sync(0xffffffffu, need);
+        if (lane == 0) s_wcount[warp] = __popc(bal);
         __syncthreads();
-        // index of the last head in the CTA (or -1)
-        int last_head = -1;
+        uint32_t off = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < T / 32; w++)
-            if (s_wcount[w]) last_head = w * 32 + 31 - __clz(s_wcount[w]);
-        const bool in_tail = si.valid && tid >= last_head;  // last_head = -1: every valid thread
-        uint32_t v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            v[i] = in_tail ? own[i] : 0u;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        for (int w = 0; w < T / 32; w++) {
+            uint32_t cw = s_wcount[w];
+            if (w < warp) off += cw;
+            total += cw;
+        }
+        if (total == 0) break;
+        if (need) {
+            s_entry[tid] = want;
+            s_list[off + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)tid;
+            dirty = true;
         }
         __syncthreads();
-        if (lane == 0) { s_tail[warp][0] = v[0]; s_tail[warp][1] = v[1]; s_tail[warp][2] = v[2]; s_tail[warp][3] = v[3]; }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t tot[4];
-            for (int i = 0; i < 4; i++) {
-                tot[i] = (last_head < 0) ? s_carry[i] : 0u;
-                for (int w = 0; w < T / 32; w++) tot[i] += s_tail[w][i];
-            }
-            const uint64_t ex = s_exit[last];
-            my_chain[0] = (uint32_t)ex;
-            my_chain[1] = (uint32_t)(ex >> 32);
-            my_chain[2] = tot[0]; my_chain[3] = tot[1]; my_chain[4] = tot[2]; my_chain[5] = tot[3];
-            __threadfence();
-            *reinterpret_cast<volatile uint32_t*>(my_chain + 6) = 1u;
-        }
-    }
-    // 4. segmented exclusive prefix over the CTA (segments start at stream heads)
-    __syncthreads();
-    s_head[tid] = head ? 1u : 0u;
-#pragma unroll
-    for (int i = 0; i < 4; i++) s_cnt[tid][i] = own[i] + ((tid == 0 && !head) ? s_carry[i] : 0u);
-    __syncthreads();
-    for (int o = 1; o < T; o <<= 1) {  // inclusive segmented scan (Hillis-Steele)
-        uint32_t a[4] = {0, 0, 0, 0};
-        uint32_t h = s_head[tid];
-        bool take = tid >= o && !h;
-        if (take) {
-            for (int i = 0; i < 4; i++) a[i] = s_cnt[tid - o][i];
-            h = s_head[tid - o];
-        }
-        __syncthreads();
-        if (take) {
-            for (int i = 0; i < 4; i++) s_cnt[tid][i] += a[i];
-            s_head[tid] = h;
+        if ((uint32_t)tid < total) {  // dense: item i is decoded by thread i
+            const int j = s_list[tid];
+            uint64_t ex;
+            SubCount k;
+            run_sub_core(sh.sc.mode, sh.ctx, glut, src, s_b0[j], s_ownr[j], s_stopr[j], s_endr[j], s_entry[j], ex, k);
+            s_exit[j] = ex;
+            s_cnt[j][0] = k.blocks; s_cnt[j][1] = (uint32_t)k.dc[0]; s_cnt[j][2] = (uint32_t)k.dc[1]; s_cnt[j][3] = (uint32_t)k.dc[2];
+            changes++;
         }
         __syncthreads();
     }
-    if (si.valid) {
-        uint4 pre = make_uint4(s_cnt[tid][0] - own[0], s_cnt[tid][1] - own[1], s_cnt[tid][2] - own[2], s_cnt[tid][3] - own[3]);
+    if (si.valid && dirty) {
         B.sub_entry[g] = s_entry[tid];
         B.sub_exit[g] = s_exit[tid];
-        reinterpret_cast<uint4*>(B.sub_count)[g] = make_uint4(own[0], own[1], own[2], own[3]);
-        reinterpret_cast<uint4*>(B.sub_prefix)[g] = pre;
+        reinterpret_cast<uint4*>(B.sub_count)[g] = make_uint4(s_cnt[tid][0], s_cnt[tid][1], s_cnt[tid][2], s_cnt[tid][3]);
     }
     if (changes && B.sync_changes) atomicAdd(B.sync_changes, changes);
+}
+
+// ---- fix-up, stage 2: one warp per scan ------------------------------------------------------------------
+// After stage 1 the only places where an entry state can still differ from its predecessor's exit are the
+// CTA boundaries of stage 1 (every T-th subsequence).  Lane 0 walks them in order; on a mismatch it
+// re-decodes forward from the corrected state until the exit state matches the stored entry of the next
+// subsequence (from there on everything is consistent up to the next boundary).  Then the whole warp
+// computes the segmented exclusive prefix sums (first block index and DC predictors per subsequence).
+// Nothing waits on another CTA: all scans of the batch are repaired concurrently, one thread each.
+__global__ void __launch_bounds__(128) chain_kernel(const bj_scan* __restrict__ scans, int scan_first, int n_scans,
+                                                    bj_entropy_buffers B) {
+    __shared__ CtaSharedLite shs[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int si_idx = blockIdx.x * 4 + warp;
+    if (si_idx >= n_scans) return;
+    CtaSharedLite& sh = shs[warp];
+    {
+        const uint32_t* srcw = reinterpret_cast<const uint32_t*>(&scans[scan_first + si_idx]);
+        for (int i = lane; i < (int)(sizeof(bj_scan) / 4); i += 32) reinterpret_cast<uint32_t*>(&sh.sc)[i] = srcw[i];
+        __syncwarp();
+        if (lane == 0) {
+            const bj_scan& sc = sh.sc;
+            for (int i = 0; i < BJ_MAX_SLOTS; i++) {
+                sh.ctx.dc_tab[i] = sc.slot_dc[i];
+                sh.ctx.ac_tab[i] = sc.slot_ac[i];
+                sh.ctx.slot_comp[i] = sc.slot_comp[i];
+            }
+            sh.ctx.nslots = sc.nslots;
+            sh.ctx.ss = sc.ss;
+            sh.ctx.se = sc.se;
+            sh.ctx.al = sc.al;
+            uint32_t last = sc.stream0 + sc.n_streams - 1;
+            uint64_t bits = (B.stream_end[last] - B.stream_start[last]) * 8;
+            sh.scan_nsub = B.stream_sub[last] + (uint32_t)((bits + S - 1) / S);
+        }
+        __syncwarp();
+    }
+    const uint32_t nsub = sh.scan_nsub;
+    const size_t g0 = sh.sc.sub0;
+    if (lane == 0) {
+        GlobalSrc src{B.words, (uint32_t)B.words_len};
+        const uint32_t* const glut = B.lut + sh.sc.lut_off;
+        uint32_t repairs = 0;
+        for (uint32_t lb = T; lb < nsub; lb += T) {
+            uint32_t cur = lb;
+            uint64_t st = B.sub_exit[g0 + cur - 1];
+            if (B.sub_entry[g0 + cur] == st) continue;
+            for (;;) {
+                SubInfo si = locate(sh, B, cur);
+                if (!si.valid || si.l == 0) break;  // a stream head has a known entry state
+                B.sub_entry[g0 + cur] = st;
+                uint64_t ex;
+                SubCount k;
+                run_sub_core(sh.sc.mode, sh.ctx, glut, src, si.b0, si.own_rel, si.stop_rel, si.end_rel, st, ex, k);
+                B.sub_exit[g0 + cur] = ex;
+                reinterpret_cast<uint4*>(B.sub_count)[g0 + cur] = make_uint4(k.blocks, (uint32_t)k.dc[0], (uint32_t)k.dc[1], (uint32_t)k.dc[2]);
+                repairs++;
+                cur++;
+                if (cur >= nsub || B.sub_entry[g0 + cur] == ex) break;
+                st = ex;
+            }
+        }
+        if (repairs && B.sync_changes) atomicAdd(B.sync_changes, repairs);
+    }
+    __syncwarp();
+    __threadfence_block();
+    // segmented exclusive prefix sums: segments start at stream heads
+    uint32_t carry[4] = {0, 0, 0, 0};
+    for (uint32_t base = 0; base < nsub; base += 32) {
+        const uint32_t l = base + lane;
+        uint4 c = make_uint4(0, 0, 0, 0);
+        if (l < nsub) c = reinterpret_cast<const uint4*>(B.sub_count)[g0 + l];
+        // is l a stream head?  (stream_sub is increasing; several heads may fall into one group of 32)
+        bool is_head = false;
+        if (l < nsub) {
+            if (l == 0) is_head = true;
+            else if (sh.sc.n_streams > 1) {
+                uint32_t lo = 0, hi = sh.sc.n_streams - 1;
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi + 1) >> 1;
+                    if (B.stream_sub[sh.sc.stream0 + mid] <= l) lo = mid;
+                    else hi = mid - 1;
+                }
+                is_head = B.stream_sub[sh.sc.stream0 + lo] == l;
+            }
+        }
+        uint32_t v[4] = {c.x, c.y, c.z, c.w};
+        uint32_t h = is_head ? 1u : 0u;
+        if (lane == 0 && !is_head)
+            for (int i = 0; i < 4; i++) v[i] += carry[i];
+        const uint32_t own[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {  // inclusive segmented warp scan
+            uint32_t pv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) pv[i] = __shfl_up_sync(0xffffffffu, v[i], o);
+            uint32_t ph = __shfl_up_sync(0xffffffffu, h, o);
+            if (lane >= o && !h) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] += pv[i];
+                h = ph;
+            }
+        }
+        if (l < nsub)
+            reinterpret_cast<uint4*>(B.sub_prefix)[g0 + l] = make_uint4(v[0] - own[0], v[1] - own[1], v[2] - own[2], v[3] - own[3]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) carry[i] = __shfl_sync(0xffffffffu, v[i], 31);
+    }
 }
 
 // ---- writing pass ------------------------------------------------------------------------------------
@@ -651,7 +667,8 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
     const uint32_t lut_cap = max_lut < (uint32_t)kMaxLutSmem ? max_lut : (uint32_t)kMaxLutSmem;
     const size_t smem = cta_smem_bytes(lut_cap);
     if (mode == BJ_MODE_BASELINE || mode == BJ_MODE_DC_FIRST || mode == BJ_MODE_AC_FIRST) {
-        if (!chain || max_sub == 0) return BJ_E_ARG;
+        (void)chain;
+        if (max_sub == 0) return BJ_E_ARG;
         e = cudaFuncSetAttribute(spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
@@ -659,9 +676,8 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         if (grid.y > 65535) return BJ_E_ARG;
         if (phases & BJ_PHASE_SPEC) spec_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
         if (phases & BJ_PHASE_FIX) {
-            e = cudaMemsetAsync(chain, 0, sizeof(uint32_t) * kChainWords * (size_t)grid.x * grid.y, st);
-            if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/memset");
-            fix_kernel<<<grid, T, 0, st>>>(scans, scan_first, *bufs, chain);
+            fix_local_kernel<<<grid, T, 0, st>>>(scans, scan_first, *bufs);
+            chain_kernel<<<(n_scans + 3) / 4, 128, 0, st>>>(scans, scan_first, n_scans, *bufs);
         }
         if (phases & BJ_PHASE_WRITE) write_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
     } else if (mode == BJ_MODE_DC_REFINE) {
