@@ -319,10 +319,11 @@ def main():
     dom = max((k for k in stages if "gbs" in stages[k]), key=lambda k: stages[k]["ms"])
     # dram__bytes_read.sum + dram__bytes_write.sum per image from the ncu --set full captures under profiles/
     # (r1b, 64 images per launch): measured DRAM traffic, scaled to the images one launch of this run covers
-    ncu_traffic_per_image = {"pixels": (402.810112e6 + 355.376896e6) / 64, "write": (30.704896e6 + 347.687424e6) / 64,
-                             "spec": 24.409856e6 / 64, "fix": 30.578176e6 / 64}
+    ncu_traffic_per_image = {"pixels": (401.201920e6 + 363.742976e6) / 64, "write": (32.204544e6 + 349.324032e6) / 64,
+                             "spec": 24.421376e6 / 64, "fix": (19.857408e6 + 3.593472e6) / 64,
+                             "unstuff": (24.596224e6 + 24.657920e6) / 64}
     img_per_launch = n_img / n_chunks
-    names = {"unstuff": "unstuff_count/scan_tiles/unstuff_scatter", "spec": "spec_kernel", "fix": "fix_kernel",
+    names = {"unstuff": "unstuff_count/scan_tiles/unstuff_scatter", "spec": "spec_kernel", "fix": "fix_local_kernel + chain_kernel",
              "write": "write_kernel", "pixels": "bj_pixels_fast_kernel<2,2,3> (fused dezigzag+dequant+IDCT+upsample+colour)"}
 
     def roof(k):
@@ -330,7 +331,7 @@ def main():
         tr = ncu_traffic_per_image.get(k)
         return {"kernel": names[k], "bound": "hbm", "achieved": st.get("gbs"), "peak": peak, "unit": "GB/s",
                 "frac": st.get("frac_of_peak"), "traffic": (tr * img_per_launch) if tr else None,
-                "traffic_source": "ncu --set full capture profiles/r1b_full_summary.csv, scaled per image",
+                "traffic_source": "ncu --set full capture profiles/r1_final_full_summary.csv (64 images), scaled per image",
                 "peak_source": peak_src, "launches_per_step": n_chunks,
                 "algorithmic_bytes_per_launch": alg[k] / n_chunks, "ms_per_launch": st.get("ms", 0.0) / n_chunks,
                 "share_of_step": st.get("share_of_step")}

@@ -422,28 +422,43 @@ __global__ void __launch_bounds__(128) chain_kernel(const bj_scan* __restrict__ 
     }
     const uint32_t nsub = sh.scan_nsub;
     const size_t g0 = sh.sc.sub0;
-    if (lane == 0) {
+    {
+        // Lane i owns boundary lb = (i + 1) * T (+ 32 * T * k): it may only rewrite subsequences of its own
+        // range [lb, lb + T), so lanes never race; a correction that reaches the end of the range is picked
+        // up by the owner of the next boundary in the next pass.  Passes repeat until nothing mismatches.
         GlobalSrc src{B.words, (uint32_t)B.words_len};
         const uint32_t* const glut = B.lut + sh.sc.lut_off;
         uint32_t repairs = 0;
-        for (uint32_t lb = T; lb < nsub; lb += T) {
-            uint32_t cur = lb;
-            uint64_t st = B.sub_exit[g0 + cur - 1];
-            if (B.sub_entry[g0 + cur] == st) continue;
-            for (;;) {
-                SubInfo si = locate(sh, B, cur);
-                if (!si.valid || si.l == 0) break;  // a stream head has a known entry state
-                B.sub_entry[g0 + cur] = st;
-                uint64_t ex;
-                SubCount k;
-                run_sub_core(sh.sc.mode, sh.ctx, glut, src, si.b0, si.own_rel, si.stop_rel, si.end_rel, st, ex, k);
-                B.sub_exit[g0 + cur] = ex;
-                reinterpret_cast<uint4*>(B.sub_count)[g0 + cur] = make_uint4(k.blocks, (uint32_t)k.dc[0], (uint32_t)k.dc[1], (uint32_t)k.dc[2]);
-                repairs++;
-                cur++;
-                if (cur >= nsub || B.sub_entry[g0 + cur] == ex) break;
-                st = ex;
+        for (;;) {
+            bool any = false;
+            for (uint32_t lb0 = T; lb0 < nsub; lb0 += 32 * T) {
+                const uint32_t lb = lb0 + lane * T;
+                if (lb < nsub) {
+                    uint32_t cur = lb;
+                    uint64_t st = B.sub_exit[g0 + cur - 1];
+                    if (B.sub_entry[g0 + cur] != st) {
+                        const uint32_t lim = min(lb + (uint32_t)T, nsub);
+                        for (;;) {
+                            SubInfo si = locate(sh, B, cur);
+                            if (!si.valid || si.l == 0) break;  // a stream head has a known entry state
+                            B.sub_entry[g0 + cur] = st;
+                            uint64_t ex;
+                            SubCount k;
+                            run_sub_core(sh.sc.mode, sh.ctx, glut, src, si.b0, si.own_rel, si.stop_rel, si.end_rel, st, ex, k);
+                            B.sub_exit[g0 + cur] = ex;
+                            reinterpret_cast<uint4*>(B.sub_count)[g0 + cur] =
+                                make_uint4(k.blocks, (uint32_t)k.dc[0], (uint32_t)k.dc[1], (uint32_t)k.dc[2]);
+                            repairs++;
+                            any = true;
+                            cur++;
+                            if (cur >= lim || B.sub_entry[g0 + cur] == ex) break;
+                            st = ex;
+                        }
+                    }
+                }
             }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, any)) break;
         }
         if (repairs && B.sync_changes) atomicAdd(B.sync_changes, repairs);
     }
