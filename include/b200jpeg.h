@@ -224,6 +224,15 @@ int bj_pixels_fast_strip(int layout); /* MCUs per CTA the specialised pixel kern
 const char* bj_last_cuda_error(void);
 
 /*
+ * Host-side helpers for the Python marker walk (no GPU involved).
+ *   bj_host_find_marker  first p >= pos with data[p] == 0xFF and data[p+1] not 0x00 / RSTn: the end of an
+ *                        entropy-coded segment as the reference's main loop sees it (jpeg_decoder.py:93)
+ *   bj_host_count_sos    bytes.count(SOS) of jpeg_decoder.py:635-637
+ */
+uint64_t bj_host_find_marker(const uint8_t* data, uint64_t n, uint64_t pos);
+uint32_t bj_host_count_sos(const uint8_t* data, uint64_t n, uint64_t pos);
+
+/*
  * Pixel stages.  Replaces, for a whole batch of images in one launch:
  *   undo_zigzag * Q              jpeg_decoder.py:1648-1662, :869, :1347-1348   (int16 product wraps)
  *   InverseDCT.__call__          :1561-1573   (fp64 sum in numpy's pairwise order, round-half-even, +128)

@@ -23,6 +23,43 @@ _SEGMENT_END = re.compile(rb"\xff[^\x00\xd0-\xd7]")
 _SOS = b"\xff\xda"
 _DNL = b"\xff\xdc"
 
+_HOST = None
+
+
+def _host_lib():
+    """The C helpers of libb200jpeg.so (memchr-based scans), or False when the library is not built
+    (the pure-Python scan is used then: parsing never needs a GPU)."""
+    global _HOST
+    if _HOST is None:
+        try:
+            import ctypes
+            from .build import LIB
+            L = ctypes.CDLL(str(LIB))
+            L.bj_host_find_marker.restype = ctypes.c_uint64
+            L.bj_host_find_marker.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64]
+            L.bj_host_count_sos.restype = ctypes.c_uint32
+            L.bj_host_count_sos.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64]
+            _HOST = L
+        except (OSError, AttributeError):
+            _HOST = False
+    return _HOST
+
+
+def find_segment_end(data: bytes, pos: int) -> int:
+    """End of the entropy-coded segment that starts at pos: the first 0xFF not followed by 0x00 / RSTn."""
+    L = _host_lib()
+    if L:
+        return int(L.bj_host_find_marker(data, len(data), pos))
+    mt = _SEGMENT_END.search(data, pos)
+    return mt.start() if mt else len(data)
+
+
+def count_sos(data: bytes, pos: int) -> int:
+    L = _host_lib()
+    if L:
+        return int(L.bj_host_count_sos(data, len(data), pos))
+    return data.count(_SOS, pos)
+
 
 @dataclass(frozen=True)
 class HuffSpec:
@@ -203,15 +240,14 @@ def parse_jpeg(data: bytes) -> ParsedJpeg:
                     raise CorruptedJpeg("Image height cannot be zero.")
                 p.height = _be16(data, d + 4)
             if not p.scans:
-                p.scan_amount = data.count(_SOS, pos) + 1           # (:635-637)
+                p.scan_amount = count_sos(data, pos) + 1            # (:635-637)
                 _set_geometry(p)
             sc = Scan(comps=tuple(comps), td=tuple(td), ta=tuple(ta), ss=ss, se=se, ah=ah, al=al, ri=ri,
                       data_start=pos, data_end=n,
                       dc_specs=tuple(huff.get(t_) for t_ in td),
                       ac_specs=tuple(huff.get(0x10 | t_) for t_ in ta))
             _classify_scan(p, sc)
-            mt = _SEGMENT_END.search(data, pos)
-            sc.data_end = mt.start() if mt else n
+            sc.data_end = find_segment_end(data, pos)
             pos = sc.data_end
             p.scans.append(sc)
         else:
