@@ -232,6 +232,21 @@ const char* bj_last_cuda_error(void);
 uint64_t bj_host_find_marker(const uint8_t* data, uint64_t n, uint64_t pos);
 uint32_t bj_host_count_sos(const uint8_t* data, uint64_t n, uint64_t pos);
 
+/* One entry of the byte-level marker walk: a marker segment (payload [start, end), marker = second marker
+ * byte) or an entropy-coded run (marker = 0x100).  Offsets are relative to the start of the file. */
+typedef struct bj_host_entry {
+    uint64_t start, end;
+    uint32_t marker;
+    uint32_t reserved;
+} bj_host_entry;
+
+/* Byte-level marker walk of one file, mirroring the main loop of jpeg_decoder.py:78-110 (segments are
+ * located, not interpreted).  Returns the number of entries, -1: not a JPEG, -2: more than max_entries. */
+int bj_host_walk(const uint8_t* data, uint64_t n, bj_host_entry* entries, int max_entries);
+/* The same for n_files files of one buffer on n_threads host threads (entries: [n_files][max_entries]). */
+void bj_host_walk_batch(const uint8_t* raw, const uint64_t* off, const uint64_t* size, int n_files,
+                        bj_host_entry* entries, int max_entries, int32_t* counts, int n_threads);
+
 /*
  * Pixel stages.  Replaces, for a whole batch of images in one launch:
  *   undo_zigzag * Q              jpeg_decoder.py:1648-1662, :869, :1347-1348   (int16 product wraps)

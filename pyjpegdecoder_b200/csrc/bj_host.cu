@@ -43,3 +43,74 @@ uint32_t bj_host_count_sos(const uint8_t* data, uint64_t n, uint64_t pos) {
 }
 
 }  // extern "C"
+
+// ---- batch marker walk ---------------------------------------------------------------------------------
+// Mirrors the control flow of JpegDecoder.__init__ (jpeg_decoder.py:78-110) at the byte level only: it
+// reports where every segment and every entropy-coded run lies; interpreting the segment payloads stays
+// in Python (parser.py).  Entries: marker 0x100 = entropy-coded run [start, end); otherwise a marker
+// segment whose payload is [start, end) (start points after the 2-byte length).  Returns the number of
+// entries, or -1 if the file does not start with FFD8FF, or -2 if max_entries is too small.
+#include <thread>
+#include <vector>
+
+static int walk_one(const uint8_t* d, uint64_t n, bj_host_entry* out, int max_entries) {
+    if (n < 3 || d[0] != 0xFF || d[1] != 0xD8 || d[2] != 0xFF) return -1;
+    int k = 0;
+    uint64_t pos = 2;
+    for (;;) {
+        if (pos >= n) break;
+        const uint8_t* q = (const uint8_t*)memchr(d + pos, 0xFF, (size_t)(n - pos));
+        if (!q) break;
+        pos = (uint64_t)(q - d);
+        if (pos + 1 >= n) break;
+        uint32_t m = d[pos + 1];
+        pos += 2;
+        if (m == 0x00 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (k >= max_entries) return -2;
+        if (m == 0xD9) {
+            out[k++] = bj_host_entry{pos, pos, m, 0};
+            break;
+        }
+        if (pos + 2 > n) break;
+        uint64_t size = ((uint64_t)d[pos] << 8 | d[pos + 1]);
+        size = size >= 2 ? size - 2 : 0;
+        pos += 2;
+        uint64_t end = pos + size < n ? pos + size : n;
+        out[k++] = bj_host_entry{pos, end, m, 0};
+        if (m == 0xDD) {
+            pos += 2;  // the reference advances by 2, not by the segment length (:476-477)
+        } else if (m == 0xDA) {
+            pos += size;
+            if (k >= max_entries) return -2;
+            uint64_t e = bj_host_find_marker(d, n, pos);
+            out[k++] = bj_host_entry{pos, e, 0x100, 0};
+            pos = e;
+        } else {
+            pos += size;
+        }
+    }
+    return k;
+}
+
+extern "C" int bj_host_walk(const uint8_t* data, uint64_t n, bj_host_entry* entries, int max_entries) {
+    return walk_one(data, n, entries, max_entries);
+}
+
+// Walk n_files files stored in one buffer (file i = raw[off[i], off[i] + size[i])) with n_threads host
+// threads.  entries: [n_files][max_entries]; counts[i] = result of bj_host_walk for file i.
+extern "C" void bj_host_walk_batch(const uint8_t* raw, const uint64_t* off, const uint64_t* size, int n_files,
+                                   bj_host_entry* entries, int max_entries, int32_t* counts, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_files) n_threads = n_files > 0 ? n_files : 1;
+    auto work = [&](int t) {
+        for (int i = t; i < n_files; i += n_threads)
+            counts[i] = walk_one(raw + off[i], size[i], entries + (size_t)i * max_entries, max_entries);
+    };
+    if (n_threads == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+}

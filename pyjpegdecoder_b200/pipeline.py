@@ -30,6 +30,9 @@ ENTROPY_THREADS = 128
 UNSTUFF_TILE = 4096
 MAX_SLOTS = 10
 
+# batches of at least this many files are planned by fastplan.py (C marker walk + templates)
+FAST_PLAN_MIN_FILES = 4
+
 MODES = {"baseline": 0, "dc_first": 1, "dc_refine": 2, "ac_first": 3, "ac_refine": 4}
 
 # numpy mirror of struct bj_scan (144 bytes, see include/b200jpeg.h)
@@ -37,12 +40,12 @@ SCAN_DTYPE = np.dtype({
     "names": ["raw_off", "coef_block0", "raw_len", "image", "stream0", "n_streams", "ri", "n_mcu", "mcus_x",
               "sub0", "n_sub_max", "lut_off", "lut_len", "tile0", "frame_mcus_x", "frame_bpm", "nslots", "mode",
               "ss", "se", "ah", "al", "interleaved", "comp_h", "comp_v", "comp_slot0", "ncomp_scan",
-              "slot_frame", "slot_comp", "slot_dc", "slot_ac", "reserved"],
+              "slot_frame", "slot_comp", "slot_dc", "slot_ac", "pad0", "reserved"],
     "formats": ["<u8", "<u8", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4",
                 "<u2", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1", "u1",
-                ("u1", (MAX_SLOTS,)), ("u1", (MAX_SLOTS,)), ("<u2", (MAX_SLOTS,)), ("<u2", (MAX_SLOTS,)), "<u4"],
+                ("u1", (MAX_SLOTS,)), ("u1", (MAX_SLOTS,)), ("<u2", (MAX_SLOTS,)), ("<u2", (MAX_SLOTS,)), "<u2", "<u4"],
     "offsets": [0, 8, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 66, 67, 68, 69, 70, 71, 72, 73, 74, 75,
-                76, 77, 78, 88, 98, 118, 140],
+                76, 77, 78, 88, 98, 118, 138, 140],
     "itemsize": 144,
 })
 
@@ -186,14 +189,28 @@ class BatchPlan:
                              if g.mode in (0, 1, 3)) if any(g.mode in (0, 1, 3) for g in self.groups) else 1
 
 
-def pack_files(datas: Sequence[bytes], pin: bool = True) -> Tuple[torch.Tensor, List[int]]:
-    """Concatenate file images into one (pinned) host buffer, each file 16-byte aligned."""
+_PINNED_POOL: Dict[int, torch.Tensor] = {}
+
+
+def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot: Optional[int] = None) -> Tuple[torch.Tensor, List[int]]:
+    """Concatenate file images into one (pinned) host buffer, each file 16-byte aligned.
+    Returns (buffer, offsets); the sizes are len(datas[i]).  reuse_slot: keep the pinned allocation in a
+    small pool and reuse it for the next batch packed into the same slot (pinning memory is slow); the
+    caller must be done with the previous batch of that slot (decode_batch synchronises before returning)."""
     offsets, total = [], 0
     for d in datas:
         offsets.append(total)
         total += (len(d) + 15) & ~15
     total += 64
-    buf = torch.empty(total, dtype=torch.uint8, pin_memory=pin and torch.cuda.is_available())
+    pinned = pin and torch.cuda.is_available()
+    if reuse_slot is not None and pinned:
+        pool = _PINNED_POOL.get(reuse_slot)
+        if pool is None or pool.numel() < total:
+            pool = torch.empty(max(total, 1 << 20) * 5 // 4, dtype=torch.uint8, pin_memory=True)
+            _PINNED_POOL[reuse_slot] = pool
+        buf = pool[:total]
+    else:
+        buf = torch.empty(total, dtype=torch.uint8, pin_memory=pinned)
     view = buf.numpy()
     for d, off in zip(datas, offsets):
         view[off:off + len(d)] = np.frombuffer(d, dtype=np.uint8)
@@ -369,12 +386,16 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
     upto_wave=k stops the entropy stage after the first k scan groups (tests: per-scan parity)."""
     require_cuda(device)
     if packed is None:
-        packed = pack_files(datas)
+        packed = pack_files(datas, reuse_slot=0 if check else None)
     raw_host, offsets = packed
     if plan is None:
-        if parsed is None:
-            parsed = [parse_jpeg(d) for d in datas]
-        plan = BatchPlan(parsed, offsets, raw_host.numel())
+        if parsed is None and datas is not None and len(datas) >= FAST_PLAN_MIN_FILES:
+            from .fastplan import plan_batch
+            plan = plan_batch(raw_host, offsets, [len(d) for d in datas])
+        else:
+            if parsed is None:
+                parsed = [parse_jpeg(d) for d in datas]
+            plan = BatchPlan(parsed, offsets, raw_host.numel())
     pipe = DevicePipeline(plan, device, stream)
     pipe.upload(raw_host)
     pipe.launch(out_kind=out_kind, upto_group=upto_wave)

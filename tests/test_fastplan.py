@@ -1,0 +1,69 @@
+"""The fast batch planner (C marker walk + per-key templates + numpy assembly) must produce exactly the
+plan that the per-file Python path produces."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_case_names
+
+
+def _both(datas):
+    from pyjpegdecoder_b200.fastplan import FastPlan
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    from pyjpegdecoder_b200.pipeline import BatchPlan, pack_files
+    raw, offs = pack_files(datas, pin=False)
+    slow = BatchPlan([parse_jpeg(d) for d in datas], offs, raw.numel())
+    fast = FastPlan(raw.numpy(), offs, [len(d) for d in datas], threads=4)
+    return slow, fast
+
+
+def _assert_same(slow, fast):
+    assert slow.scans.dtype == fast.scans.dtype and slow.geom.images.dtype == fast.geom.images.dtype
+    # byte-level: these arrays are uploaded as raw struct bj_scan[] / bj_image[]
+    assert np.array_equal(np.ascontiguousarray(slow.scans).view(np.uint8), np.ascontiguousarray(fast.scans).view(np.uint8))
+    assert np.array_equal(np.ascontiguousarray(slow.geom.images).view(np.uint8),
+                          np.ascontiguousarray(fast.geom.images).view(np.uint8))
+    assert np.array_equal(slow.geom.qtabs, fast.geom.qtabs)
+    assert np.array_equal(slow.tile_scan, fast.tile_scan)
+    assert np.array_equal(slow.lut, fast.lut)
+    for a in ("n_streams", "n_sub", "n_tiles", "max_chain", "any_progressive", "raw_bytes"):
+        assert getattr(slow, a) == getattr(fast, a), a
+    for a in ("total_blocks", "out_bytes", "max_strips", "layout_mask", "block_offsets", "out_offsets", "out_shapes"):
+        assert getattr(slow.geom, a) == getattr(fast.geom, a), a
+    assert [vars(g) for g in slow.groups] == [vars(g) for g in fast.groups]
+    assert len(slow.parsed) == len(fast.parsed)
+    for p, q in zip(slow.parsed, fast.parsed):
+        assert (p.width, p.height, p.progressive, p.file_size) == (q.width, q.height, q.progressive, q.file_size)
+        assert [(s.data_start, s.data_end, s.kind) for s in p.scans] == [(s.data_start, s.data_end, s.kind) for s in q.scans]
+
+
+def test_fastplan_equals_batchplan_on_all_fixtures():
+    datas = [(GOLDEN / "cases" / f"{n}.jpg").read_bytes() for n in golden_case_names()]
+    _assert_same(*_both(datas))
+
+
+def test_fastplan_with_repeated_and_interleaved_files():
+    names = ["base_120x88_ss2", "prog_97x61_ss1_dri5", "base_gray_70x50", "base_120x88_ss2", "prog_97x61_ss1_dri5",
+             "base_97x61_ss0_dri13", "base_120x88_ss2"]
+    datas = [(GOLDEN / "cases" / f"{n}.jpg").read_bytes() for n in names]
+    _assert_same(*_both(datas))
+
+
+def test_fastplan_big_file():
+    data = (GOLDEN / "base_image.jpg").read_bytes()
+    _assert_same(*_both([data, data]))
+
+
+def test_fastplan_raises_like_the_parser():
+    from pyjpegdecoder_b200 import NotJpeg, UnsupportedJpeg
+    from pyjpegdecoder_b200.fastplan import FastPlan
+    from pyjpegdecoder_b200.pipeline import pack_files
+    good = (GOLDEN / "cases" / "base_70x50_ss2.jpg").read_bytes()
+    bad = bytearray(good)
+    i = good.find(b"\xff\xc0")
+    bad[i + 4] = 12
+    raw, offs = pack_files([good, bytes(bad)], pin=False)
+    with pytest.raises(UnsupportedJpeg):
+        FastPlan(raw.numpy(), offs, [len(good), len(bad)])
+    raw, offs = pack_files([good, b"\x89PNG-not-a-jpeg"], pin=False)
+    with pytest.raises(NotJpeg):
+        FastPlan(raw.numpy(), offs, [len(good), 15])
