@@ -154,6 +154,8 @@ typedef struct bj_entropy_buffers {
     int16_t* coef;
     uint32_t* err;          /* per image error word (BJ_ERR_*) */
     uint32_t* sync_changes; /* optional statistics: subsequences re-decoded by the fix-up pass */
+    uint32_t* blk_pos;      /* one per coefficient block; only needed (non-NULL) when the batch has AC
+                               refinement scans: where each block's data starts in its stream */
 } bj_entropy_buffers;
 
 /*
@@ -187,7 +189,7 @@ bj_status bj_entropy_plan(const bj_scan* scans, int scan_first, int n_scans, con
  * Progressive images need their coefficient blocks zeroed before the first scan.
  *   max_sub      max over the wave's scans of n_sub_max         (baseline / DC first / AC first)
  *   max_streams  max over the wave's scans of n_streams         (AC refine)
- *   max_blocks   max over the wave's scans of n_mcu * nslots    (DC refine)
+ *   max_blocks   max over the wave's scans of n_mcu * nslots    (DC refine, AC refine)
  *   max_lut      max over the wave's scans of lut_len
  *   chain        reserved (may be NULL)
  *   phases       BJ_PHASE_ALL, or a subset of the three kernels of the speculative modes so that a

@@ -590,12 +590,13 @@ __global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ sc
         else err = base_write_run(rd, z, slot, sh.ctx, glut, si.stop_rel, si.end_rel, blk, si.nblk_stream, pred, sink);
     } else if (mode == BJ_MODE_DC_FIRST) {
         GlobalCoefSink sink{B.coef, &sh.sc, si.mcu0};
-        err = dcfirst_write_run(rd, slot, sh.ctx, ls ? sh.lut : glut, si.stop_rel, si.end_rel, blk, si.nblk_stream, pred, sink);
+        if (ls) err = dcfirst_write_run(rd, slot, sh.ctx, sh.lut, si.stop_rel, si.end_rel, blk, si.nblk_stream, pred, sink);
+        else err = dcfirst_write_run(rd, slot, sh.ctx, glut, si.stop_rel, si.end_rel, blk, si.nblk_stream, pred, sink);
     } else {
         GlobalCoefSink sink{B.coef, &sh.sc, si.mcu0};
         uint32_t adv = 0;
-        err = acfirst_run<true>(rd, z, sh.ctx, ls ? sh.lut : glut, si.own_rel, si.stop_rel, si.end_rel, blk, si.nblk_stream, adv,
-                                sink);
+        if (ls) err = acfirst_run<true>(rd, z, sh.ctx, sh.lut, si.own_rel, si.stop_rel, si.end_rel, blk, si.nblk_stream, adv, sink);
+        else err = acfirst_run<true>(rd, z, sh.ctx, glut, si.own_rel, si.stop_rel, si.end_rel, blk, si.nblk_stream, adv, sink);
     }
     // the last subsequence of a stream checks that the stream held all its blocks
     if (si.stop == si.b1) {
@@ -625,30 +626,113 @@ __global__ void __launch_bounds__(256) dcrefine_kernel(const bj_scan* __restrict
     }
 }
 
-// ---- AC refinement: sequential per stream ---------------------------------------------------------------
-struct GlobalCoefRef {
-    int16_t* coef;
-    const bj_scan* sc;
-    uint32_t mcu0;
-    __device__ __forceinline__ int16_t& at(uint32_t blk, int z) { return coef[block_address(*sc, mcu0 + blk, 0) * 64 + z]; }
-};
+// ---- AC refinement: sequential parse per stream + parallel apply per block (see bj_entropy.cuh) ---------
+// Non-zero history of a 128-byte block: eight 128-bit loads.
+__device__ __forceinline__ void load_block(const int16_t* blk, uint4 (&v)[8]) {
+    const uint4* q = reinterpret_cast<const uint4*>(blk);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = q[i];
+}
+__device__ __forceinline__ uint64_t block_mask(const uint4 (&v)[8]) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        uint32_t b = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            b |= ((w[j] & 0xFFFFu) ? 1u : 0u) << (2 * j);
+            b |= ((w[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+        }
+        if (i < 4) lo |= b << (8 * i);
+        else hi |= b << (8 * (i - 4));
+    }
+    return ((uint64_t)hi << 32) | lo;
+}
 
-__global__ void __launch_bounds__(32) acrefine_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
-                                                      uint32_t lut_cap) {
+// One warp per stream.  All lanes stage the masks of the next 32 blocks (their loads are issued before
+// lane 0 parses the current chunk, so the memory latency is off the sequential path); lane 0 parses;
+// all lanes store the start positions.
+__global__ void __launch_bounds__(32) acrefine_parse_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
+                                                            uint32_t lut_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
+    __shared__ __align__(4) uint8_t s_tab[32 * BJ_ACR_TAB_STRIDE];
+    __shared__ uint32_t s_pos[32];
+    __shared__ uint32_t s_err;
+    load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
+    const bj_scan& sc = sh.sc;
+    const uint32_t m = blockIdx.x;
+    if (m >= sc.n_streams) return;
+    const int lane = threadIdx.x;
+    GlobalSrc src{B.words, (uint32_t)B.words_len};
+    DeepReader<GlobalSrc> rd;
+    const uint64_t sb0 = B.stream_start[sc.stream0 + m] * 8, sb1 = B.stream_end[sc.stream0 + m] * 8;
+    rd.seek(&src, sb0);
+    const uint32_t end_rel = (uint32_t)(sb1 - sb0);
+    const uint32_t mcu0 = m * sc.ri;
+    const uint32_t nblk = min(sc.ri, sc.n_mcu - mcu0);
+    const bool ls = sh.lut_in_smem != 0;  // two call sites: shared-memory loads for the common case, not generic ones
+    const uint32_t* gtab = B.lut + sc.lut_off + sh.ctx.ac_tab[0];
+    const uint32_t* stab = sh.lut + sh.ctx.ac_tab[0];
+    const int ss = sh.ctx.ss, se = sh.ctx.se;
+    uint32_t eob_run = 0;
+    uint4 v[8];
+    size_t addr = 0, addr_next = 0;
+    if ((uint32_t)lane < nblk) {
+        addr_next = block_address(sc, mcu0 + lane, 0);
+        load_block(B.coef + addr_next * 64, v);
+    }
+    for (uint32_t cb = 0; cb < nblk; cb += 32) {
+        const int nb = (int)min(32u, nblk - cb);
+        addr = addr_next;
+        if (lane < nb) acrefine_build_table(block_mask(v), ss, se, s_tab + lane * BJ_ACR_TAB_STRIDE);
+        if (cb + 32 + lane < nblk) {
+            addr_next = block_address(sc, mcu0 + cb + 32 + lane, 0);
+            load_block(B.coef + addr_next * 64, v);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (ls) s_err = acrefine_parse_chunk(rd, sh.ctx, stab, end_rel, s_tab, nb, eob_run, s_pos);
+            else s_err = acrefine_parse_chunk(rd, sh.ctx, gtab, end_rel, s_tab, nb, eob_run, s_pos);
+        }
+        __syncwarp();
+        if (s_err) {
+            if (lane == 0) atomicOr(&B.err[sc.image], s_err);
+            // blocks that were not reached decode nothing: an end-of-band block at the end of the stream
+            for (uint32_t b = cb + lane; b < nblk; b += 32)
+                B.blk_pos[block_address(sc, mcu0 + b, 0)] = end_rel | BJ_ACR_IN_EOBRUN;
+            return;
+        }
+        if (lane < nb) B.blk_pos[addr] = s_pos[lane];
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) acrefine_apply_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
+                                                             uint32_t lut_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
     load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
     const bj_scan& sc = sh.sc;
-    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= sc.n_streams) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sc.n_mcu) return;
+    const uint32_t m = i / sc.ri;
+    const size_t addr = block_address(sc, i, 0);
+    int16_t* p = B.coef + addr * 64;
+    uint4 v[8];
+    load_block(p, v);
+    const uint32_t pos = B.blk_pos[addr];
+    const uint64_t sb0 = B.stream_start[sc.stream0 + m] * 8, sb1 = B.stream_end[sc.stream0 + m] * 8;
     GlobalSrc src{B.words, (uint32_t)B.words_len};
     BitReader<GlobalSrc> rd;
-    const uint64_t sb0 = B.stream_start[sc.stream0 + m] * 8, sb1 = B.stream_end[sc.stream0 + m] * 8;
-    rd.seek(&src, sb0, 0);
-    const uint32_t mcu0 = m * sc.ri;
-    const uint32_t nblk = min(sc.ri, sc.n_mcu - mcu0);
-    GlobalCoefRef cf{B.coef, &sc, mcu0};
-    uint32_t err = acrefine_stream(rd, sh.ctx, sh.lut_in_smem ? sh.lut : (B.lut + sc.lut_off), (uint32_t)(sb1 - sb0), nblk, cf);
+    rd.seek(&src, sb0, pos & ~BJ_ACR_IN_EOBRUN);
+    uint32_t eob_run = (pos & BJ_ACR_IN_EOBRUN) ? 1u : 0u;
+    const uint64_t mask = block_mask(v);
+    const uint32_t end_rel = (uint32_t)(sb1 - sb0);
+    uint32_t err;
+    if (sh.lut_in_smem) err = acrefine_block<true>(rd, sh.ctx, sh.lut + sh.ctx.ac_tab[0], end_rel, mask, eob_run, p);
+    else err = acrefine_block<true>(rd, sh.ctx, B.lut + sc.lut_off + sh.ctx.ac_tab[0], end_rel, mask, eob_run, p);
     if (err) atomicOr(&B.err[sc.image], err);
 }
 
@@ -701,11 +785,12 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         if (gx > 4096) gx = 4096;
         dcrefine_kernel<<<dim3(gx, (unsigned)n_scans), 256, 0, st>>>(scans, scan_first, *bufs);
     } else if (mode == BJ_MODE_AC_REFINE) {
-        e = cudaFuncSetAttribute(acrefine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (!bufs->blk_pos || max_streams == 0 || max_blocks == 0) return BJ_E_ARG;
+        e = cudaFuncSetAttribute(acrefine_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(acrefine_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
-        unsigned gx = (max_streams + 31) / 32;
-        if (gx == 0) gx = 1;
-        acrefine_kernel<<<dim3(gx, (unsigned)n_scans), 32, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        acrefine_parse_kernel<<<dim3(max_streams, (unsigned)n_scans), 32, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        acrefine_apply_kernel<<<dim3((max_blocks + 127) / 128, (unsigned)n_scans), 128, smem, st>>>(scans, scan_first, *bufs, lut_cap);
     } else {
         return BJ_E_ARG;
     }

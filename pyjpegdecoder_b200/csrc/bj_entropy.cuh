@@ -97,6 +97,15 @@ struct BitReader {
     BJ_HDM uint32_t peek16() const { return peek32() >> 16; }
     // n bits (1..16) that follow the first `skipn` bits (skipn + n <= 32)
     BJ_HDM uint32_t bits_after(int skipn, int n) const { return (peek32() << skipn) >> (32 - n); }
+    BJ_HDM void skip_long(uint32_t n) {  // any n
+        o += (int)n;
+        rel += n;
+        while (o >= 32) {
+            o -= 32;
+            w0 = w1;
+            w1 = src->word(next++);
+        }
+    }
     BJ_HDM void skip(int n) {  // n <= 32
         o += n;
         rel += (uint32_t)n;
@@ -333,88 +342,197 @@ BJ_HD uint32_t acfirst_run(BitReader<Src>& rd, int& z, const ScanCtx& c, const u
 }
 
 // ---- AC refinement (:1100-1115, :1183-1198, :1209-1232, :1258-1292) -------------------------------
-// Sequential over one stream: the number of correction bits after a symbol depends on which
-// coefficients of the block are already non-zero.  Coef: at(block_in_stream, zigzag) -> int16_t&.
+// The number of correction bits that follow a symbol depends on which coefficients of the block are
+// already non-zero, so a refinement stream cannot be entered at a guessed state: the bit parse is
+// sequential.  What CAN be taken off the sequential path is everything but the parse itself.  The
+// non-zero history of a block is a 64-bit mask (bit z = coefficient z is non-zero; known before the
+// scan starts), and with it a symbol costs one table lookup plus a few bit operations: "skip r
+// zero-history coefficients" is "find the (r+1)-th clear bit", the correction bits passed on the way
+// are a population count.  So the stage runs in two passes:
+//   parse (acrefine_block<false>, one lane per stream, masks staged by the whole warp): walks the
+//         symbols touching no coefficient, and records for every block the bit position where its
+//         data starts (bit 31 set: the block lies inside an end-of-band run);
+//   apply (acrefine_block<true>, one thread per block): decodes the block again from that position
+//         and performs the stores -- fully parallel.
 // Correction is the reference's `coef |= bit << Al` on the two's-complement value (:1114), which is
 // NOT the T.81 rule for negative coefficients; bit-exact parity with the reference requires it.
-template <class Src, class Coef>
-BJ_HD uint32_t acrefine_stream(BitReader<Src>& rd, const ScanCtx& c, const uint32_t* lut, uint32_t end_rel,
-                               uint32_t nblk_stream, Coef& coef) {
-    const uint32_t* tab = lut + c.ac_tab[0];
+BJ_HD int popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+BJ_HD int ctz64(uint64_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+// position of the n-th (n >= 1) set bit of x, or -1
+BJ_HD int nth_set64(uint64_t x, int n) {
+    for (int i = 1; i < n; i++) x &= x - 1;
+    return x ? ctz64(x) : -1;
+}
+
+#define BJ_ACR_IN_EOBRUN 0x80000000u  // flag in the per-block start position
+
+// The correction bits of the non-zero coefficients in `passed` (bit i = coefficient base + i), in
+// increasing zig-zag order (:1107-1115).
+template <bool APPLY, class Src>
+BJ_HD void acrefine_corrections(BitReader<Src>& rd, uint64_t passed, int base, int16_t* p, int al) {
+    int n = popc64(passed);
+    if (!APPLY) {
+        rd.skip_long((uint32_t)n);
+        return;
+    }
+    while (n > 0) {
+        const int k = n < 32 ? n : 32;
+        const uint32_t v = rd.peek32();
+        for (int i = 0; i < k; i++) {
+            const int zz = ctz64(passed);
+            passed &= passed - 1;
+            if ((v << i) & 0x80000000u) p[base + zz] = (int16_t)(p[base + zz] | (int16_t)(1 << al));
+        }
+        rd.skip(k);
+        n -= k;
+    }
+}
+
+// One block of an AC refinement stream.  m = non-zero history of the block (all 64 positions),
+// eob_run = blocks still covered by a running end-of-band run (0: the block starts with a symbol).
+// APPLY = false only advances the reader; APPLY = true also updates the block at p.
+template <bool APPLY, class Src>
+BJ_HD uint32_t acrefine_block(BitReader<Src>& rd, const ScanCtx& c, const uint32_t* tab, uint32_t end_rel, uint64_t m,
+                              uint32_t& eob_run, int16_t* p) {
     const int ss = c.ss, se = c.se, al = c.al;
-    uint32_t blk = 0;
-    while (blk < nblk_stream) {
-        int z = ss;
-        uint32_t eob_run = 0;
+    int z = ss;
+    if (eob_run == 0) {
         while (z <= se) {
             if (rd.rel > end_rel + 7) return BJ_ERR_OVERRUN;
             const uint32_t pk = rd.peek32();
-            uint32_t e = lut_lookup(tab, pk >> 16);
-            int L = ent_len(e), rs = ent_sym(e);
+            const uint32_t e = lut_lookup(tab, pk >> 16);
+            const int L = ent_len(e), rs = ent_sym(e);
             if (L == 0) return BJ_ERR_BAD_CODE;
-            int r = rs >> 4, s = rs & 15;
-            int zero_run;
-            int newval = 0;
-            if (rs == 0) {
-                rd.skip(L);
-                eob_run = 1;
-                break;
-            } else if (rs == 0xF0) {
-                rd.skip(L);
-                zero_run = 16;
-            } else if (s == 0) {
+            const int r = rs >> 4, s = rs & 15;
+            if (s == 0 && r != 15) {  // EOBn (:1144-1149); EOB0 is a run of one block
                 eob_run = (1u << r) + (r ? take_bits(pk, L, r) : 0u);
                 rd.skip(L + r);
                 break;
-            } else {
-                zero_run = r;
-                newval = extend(take_bits(pk, L, s), s);  // value bits come right after the code (:1202)
-                rd.skip(L + s);
             }
-            // skip `zero_run` zero-history coefficients, refining the non-zero ones passed (:1184-1193);
-            // their correction bits follow in the same order (:1107-1115)
-            while (zero_run > 0) {
-                if (z > 63) return BJ_ERR_COEF_INDEX;
-                int16_t& cf = coef.at(blk, z);
-                if (cf == 0) zero_run--;
-                else {
-                    cf = (int16_t)(cf | (int16_t)(rd.bits_after(0, 1) << al));
-                    rd.skip(1);
-                }
-                z++;
-            }
-            if (s) {
-                // a new coefficient lands on the next zero-history position (:1211-1215)
-                for (;;) {
-                    if (z > 63) return BJ_ERR_COEF_INDEX;
-                    int16_t& cf = coef.at(blk, z);
-                    if (cf == 0) break;
-                    cf = (int16_t)(cf | (int16_t)(rd.bits_after(0, 1) << al));
-                    rd.skip(1);
-                    z++;
-                }
-                coef.at(blk, z) = (int16_t)((uint32_t)newval << al);  // (:1225)
-                z++;
-            }
+            // skip r zero-history coefficients (16 for ZRL), refining the non-zero ones passed
+            // (:1184-1193); with s != 0 go on to the next zero-history position, where the new
+            // coefficient lands (:1211-1215).  Its value bits come right after the code (:1202).
+            int newval = 0;
+            if (s) newval = extend(take_bits(pk, L, s), s);
+            rd.skip(L + s);
+            const uint64_t rest = m >> z;
+            const uint64_t zeros = ~rest & (~0ull >> z);
+            const int idx = nth_set64(zeros, s ? r + 1 : 16);
+            if (idx < 0) return BJ_ERR_COEF_INDEX;
+            acrefine_corrections<APPLY>(rd, rest & ((1ull << idx) - 1ull), z, p, al);
+            if (APPLY && s) p[z + idx] = (int16_t)((uint32_t)newval << al);  // (:1225)
+            z += idx + 1;
         }
-        if (z > se) {
-            blk++;
+        if (z > se) return 0;
+    }
+    // end-of-band run: the rest of this band (and the whole band of the blocks that follow inside the
+    // run) only carries correction bits for its non-zero coefficients (:1258-1292)
+    const uint64_t band = (~0ull << z) & (~0ull >> (63 - se));
+    acrefine_corrections<APPLY>(rd, m & band, 0, p, al);
+    eob_run--;
+    return rd.rel > end_rel + 7 ? BJ_ERR_OVERRUN : 0u;
+}
+
+// ---- the sequential parse, made as short as a single lane allows -----------------------------------
+// Per block the warp prepares a small table from the non-zero mask: zpos[k] = zig-zag position of the
+// k-th zero-history coefficient at or after Ss (0xFF: none), and the number of non-zero coefficients
+// in the band.  With j = zero-history coefficients consumed so far, a symbol with run r lands on
+// zpos[j + r], and the correction bits passed since the previous landing are the non-zero
+// coefficients in between: (zpos[t] - t) - (previous zpos - previous t).  One table lookup for the
+// code, one for the landing, a handful of integer operations -- no loop over coefficients.
+#define BJ_ACR_TAB_STRIDE 100  // bytes per block table; 25 words: conflict-free when lanes fill theirs
+#define BJ_ACR_TAB_NZ 80       // index of the band's non-zero count
+
+BJ_HD void acrefine_build_table(uint64_t m, int ss, int se, uint8_t* t) {
+    uint64_t zm = ~m & (~0ull << ss);
+    int k = 0;
+    while (zm) {
+        t[k++] = (uint8_t)ctz64(zm);
+        zm &= zm - 1;
+    }
+    for (; k < BJ_ACR_TAB_NZ; k++) t[k] = 0xFF;
+    t[BJ_ACR_TAB_NZ] = (uint8_t)popc64(m & (~0ull << ss) & (~0ull >> (63 - se)));
+}
+
+// Bit reader with one more word of look-ahead than BitReader: the word fetched at a refill is not
+// needed before the refill after it, which keeps the fetch latency off the parse's dependency chain.
+template <class Src>
+struct DeepReader {
+    const Src* src;
+    uint32_t w0, w1, w2;
+    int o;
+    uint32_t next, rel;
+    BJ_HDM void seek(const Src* s, uint64_t base_bit) {
+        src = s;
+        rel = 0;
+        uint32_t w = (uint32_t)(base_bit >> 5);
+        o = (int)(base_bit & 31);
+        w0 = src->word(w);
+        w1 = src->word(w + 1);
+        w2 = src->word(w + 2);
+        next = w + 3;
+    }
+    BJ_HDM uint32_t peek32() const { return funnel_left(w0, w1, o); }
+    BJ_HDM void skip(uint32_t n) {  // any n
+        o += (int)n;
+        rel += n;
+        while (o >= 32) {
+            o -= 32;
+            w0 = w1;
+            w1 = w2;
+            w2 = src->word(next++);
+        }
+    }
+};
+
+// Parse pass over a chunk of nb consecutive blocks: tabs + i * BJ_ACR_TAB_STRIDE = table of block i;
+// pos[i] receives where block i starts (relative bit position | BJ_ACR_IN_EOBRUN).
+template <class Src>
+BJ_HD uint32_t acrefine_parse_chunk(DeepReader<Src>& rd, const ScanCtx& c, const uint32_t* tab, uint32_t end_rel,
+                                    const uint8_t* tabs, int nb, uint32_t& eob_run, uint32_t* pos) {
+    const int ss = c.ss, se = c.se;
+    for (int i = 0; i < nb; i++) {
+        const uint8_t* t = tabs + i * BJ_ACR_TAB_STRIDE;
+        if (rd.rel > end_rel + 7) return BJ_ERR_OVERRUN;
+        if (eob_run) {
+            pos[i] = rd.rel | BJ_ACR_IN_EOBRUN;
+            rd.skip(t[BJ_ACR_TAB_NZ]);
+            eob_run--;
             continue;
         }
-        // end-of-band run: the rest of this band and the bands of the next eob_run-1 blocks only
-        // carry correction bits for their non-zero coefficients (:1258-1292)
-        while (eob_run > 0 && blk < nblk_stream) {
-            for (; z <= se; z++) {
-                int16_t& cf = coef.at(blk, z);
-                if (cf != 0) {
-                    if (rd.rel > end_rel + 7) return BJ_ERR_OVERRUN;
-                    cf = (int16_t)(cf | (int16_t)(rd.bits_after(0, 1) << al));
-                    rd.skip(1);
-                }
+        pos[i] = rd.rel;
+        int j = 0;     // zero-history coefficients consumed
+        int cd = ss;   // ss + non-zero coefficients refined so far
+        for (;;) {
+            const uint32_t pk = rd.peek32();
+            const uint32_t e = lut_lookup(tab, pk >> 16);
+            const int L = ent_len(e), rs = ent_sym(e);
+            if (L == 0) return BJ_ERR_BAD_CODE;
+            const int r = rs >> 4, s = rs & 15;
+            if (s == 0 && r != 15) {
+                eob_run = (1u << r) + (r ? take_bits(pk, L, r) : 0u) - 1u;
+                rd.skip((uint32_t)(L + r + (int)t[BJ_ACR_TAB_NZ] - (cd - ss)));
+                break;
             }
-            eob_run--;
-            blk++;
-            z = ss;
+            const int tt = j + r;  // ZRL: the 16th zero from here (r = 15)
+            const int zp = t[tt];
+            if (zp == 0xFF) return BJ_ERR_COEF_INDEX;
+            rd.skip((uint32_t)(ent_total(e) + (zp - tt) - cd));
+            cd = zp - tt;
+            j = tt + 1;
+            if (zp >= se) break;
         }
     }
     return 0;

@@ -57,7 +57,7 @@ class EntropyBuffers(ctypes.Structure):
                 ("sub_entry", ctypes.c_void_p), ("sub_exit", ctypes.c_void_p),
                 ("sub_count", ctypes.c_void_p), ("sub_prefix", ctypes.c_void_p),
                 ("lut", ctypes.c_void_p), ("coef", ctypes.c_void_p), ("err", ctypes.c_void_p),
-                ("sync_changes", ctypes.c_void_p)]
+                ("sync_changes", ctypes.c_void_p), ("blk_pos", ctypes.c_void_p)]
 
 
 _BOUND = False
@@ -290,12 +290,16 @@ class DevicePipeline:
                 self.coef = torch.empty((g.total_blocks, 64), dtype=torch.int16, device=dev)
                 self.err = torch.zeros(len(plan.parsed), dtype=torch.int32, device=dev)
                 self.sync_changes = torch.zeros(1, dtype=torch.int32, device=dev)
+                # per-block start positions, only for batches with AC refinement scans
+                self.blk_pos = (torch.empty(g.total_blocks, dtype=torch.int32, device=dev)
+                                if any(grp.mode == 4 for grp in plan.groups) else None)
                 self.out = None
         self.B = EntropyBuffers(self.words.data_ptr(), self.words_len, self.stream_start.data_ptr(),
                                 self.stream_end.data_ptr(), self.stream_sub.data_ptr(), self.sub_entry.data_ptr(),
                                 self.sub_exit.data_ptr(), self.sub_count.data_ptr(), self.sub_prefix.data_ptr(),
                                 self.lut.data_ptr(), self.coef.data_ptr(), self.err.data_ptr(),
-                                self.sync_changes.data_ptr())
+                                self.sync_changes.data_ptr(),
+                                self.blk_pos.data_ptr() if self.blk_pos is not None else None)
         self.kernel_launches_per_step = 0
 
     def device_bytes(self) -> int:
@@ -356,10 +360,10 @@ class DevicePipeline:
                         timed("write", lambda: call(4))
                     else:
                         timed("other_scans" if grp.mode else "entropy", lambda: call(7))
-                    n_launch += 3
+                    n_launch += 4
                 else:
                     timed("other_scans", lambda: call(7))
-                    n_launch += 1
+                    n_launch += 2 if grp.mode == 4 else 1
             if self.out is None or self._out_kind != out_kind:
                 self.out = None
             holder = {}

@@ -2,6 +2,7 @@
 // sequential emulation of the kernel orchestration in bj_entropy.cu (speculate -> fix-up rounds ->
 // prefix sums -> write).  TEST-ONLY: lets the CPU suite check the decode logic, the convergence of
 // the self-synchronising scheme and its bookkeeping against the oracle.  Never used by the product.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -189,19 +190,45 @@ uint32_t hs_decode_stream(const uint32_t* words, uint64_t n_words, uint64_t star
     return err;
 }
 
-struct HostCoef {
-    int16_t* p;
-    int16_t& at(uint32_t blk, int z) { return p[(size_t)blk * 64 + z]; }
-};
+// AC refinement the way the device runs it: a sequential parse over chunks of 32 blocks that only
+// sees the blocks' non-zero masks and records per-block start positions, then an independent
+// re-decode of every block from its recorded position (acrefine_parse_kernel / acrefine_apply_kernel).
+static uint64_t nonzero_mask(const int16_t* b) {
+    uint64_t m = 0;
+    for (int z = 0; z < 64; z++)
+        if (b[z]) m |= 1ull << z;
+    return m;
+}
 
 uint32_t hs_acrefine_stream(const uint32_t* words, uint64_t n_words, uint64_t start_byte, uint64_t end_byte,
                             const SimScan* ss_, uint32_t nblk_stream, int16_t* coef) {
     ScanCtx c = make_ctx(*ss_);
     HostSrc src{words, n_words};
-    BitReader<HostSrc> rd;
-    rd.seek(&src, start_byte * 8, 0);
-    HostCoef hc{coef};
-    return acrefine_stream(rd, c, ss_->lut, (uint32_t)((end_byte - start_byte) * 8), nblk_stream, hc);
+    const uint32_t* tab = ss_->lut + c.ac_tab[0];
+    const uint32_t end_rel = (uint32_t)((end_byte - start_byte) * 8);
+    std::vector<uint32_t> pos(nblk_stream);
+    {
+        DeepReader<HostSrc> rd;
+        rd.seek(&src, start_byte * 8);
+        uint32_t eob_run = 0;
+        for (uint32_t cb = 0; cb < nblk_stream; cb += 32) {
+            int nb = (int)std::min<uint32_t>(32, nblk_stream - cb);
+            uint8_t tabs[32 * BJ_ACR_TAB_STRIDE];
+            for (int i = 0; i < nb; i++)
+                acrefine_build_table(nonzero_mask(coef + (size_t)(cb + i) * 64), c.ss, c.se, tabs + i * BJ_ACR_TAB_STRIDE);
+            uint32_t err = acrefine_parse_chunk(rd, c, tab, end_rel, tabs, nb, eob_run, pos.data() + cb);
+            if (err) return err;
+        }
+    }
+    uint32_t err = 0;
+    for (uint32_t b = nblk_stream; b-- > 0;) {  // any order: blocks are independent now
+        BitReader<HostSrc> rd;
+        rd.seek(&src, start_byte * 8, pos[b] & ~BJ_ACR_IN_EOBRUN);
+        uint32_t eob_run = (pos[b] & BJ_ACR_IN_EOBRUN) ? 1u : 0u;
+        int16_t* p = coef + (size_t)b * 64;
+        err |= acrefine_block<true>(rd, c, tab, end_rel, nonzero_mask(p), eob_run, p);
+    }
+    return err;
 }
 
 // DC refinement (:1036-1043): bit b of the stream belongs to block b.
