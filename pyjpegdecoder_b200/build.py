@@ -54,7 +54,8 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in sources():
         obj = objdir / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        # BJ_NVCC_EXTRA: extra -D switches for tuning experiments (tools/pix_variants.sh)
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BJ_NVCC_EXTRA", "").split(), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -99,16 +99,20 @@ __device__ __noinline__ void recompute_block_exact(const Tiles<L>& t, int blk, c
     double r0[8], r1[8];
 #pragma unroll
     for (int v = 0; v < 8; v++) r0[v] = r1[v] = 0.0;
-#pragma unroll
+    // rolled over u (this path runs for about one block in a hundred: compact code matters more than its speed,
+    // the kernel's hot code has to stay inside the instruction cache)
+#pragma unroll 1
     for (int u = 0; u < 8; u++) {
+        const unsigned bits = (((u < 4) ? nz_lo : nz_hi) >> ((u & 3) * 8)) & 0xFFu;  // warp-uniform
+        if (!bits) continue;
+        const int psel = (u < 4) ? p0 : p1;
+        const double* tu = tabT + u * 8 * 64;
 #pragma unroll
         for (int v = 0; v < 8; v++) {
-            const int n = u * 8 + v;
-            const bool nz = (((n < 32) ? nz_lo : nz_hi) >> (n & 31)) & 1u;  // warp-uniform
-            if (nz) {
-                int prod = __shfl_sync(0xffffffffu, (n < 32) ? p0 : p1, n & 31);
-                double p = (double)prod;
-                const double* tt = tabT + n * 64;
+            if (bits & (1u << v)) {
+                const int prod = __shfl_sync(0xffffffffu, psel, ((u & 3) << 3) + v);
+                const double p = (double)prod;
+                const double* tt = tu + v * 64;
                 r0[v] = __dadd_rn(r0[v], __dmul_rn(p, tt[lane]));
                 r1[v] = __dadd_rn(r1[v], __dmul_rn(p, tt[lane + 32]));
             }
@@ -143,6 +147,42 @@ __device__ __noinline__ uint32_t ycc_to_rgb_exact_packed(int Yi, float Cbf, floa
 }
 
 template <int A> struct Cell { static constexpr int i = (A == 15) ? 6 : (7 * A) / 15; };
+
+// Exact colour conversion of a whole 8-pixel run, straight from the sample tile: the out-of-line, compact
+// (rolled) path behind pixel_run's tie / range guards.  Runs for a tiny fraction of the runs; what matters is
+// that it adds little code next to the hot path.
+template <class L>
+__device__ __noinline__ void pixel_run_exact(const Tiles<L>& t, int m, int r, int hx) {
+    const int ys = (r >> 3) * L::HMAX + hx, yy = r & 7;
+    const int16_t* yrow = reinterpret_cast<const int16_t*>(t.yrow(m, ys, yy));
+    unsigned char* stage = t.a + r * L::ROW_BYTES + (m * L::MCU_W + 8 * hx) * L::CH;
+    const int j = (L::VMAX == 2) ? ((r == 15) ? 6 : (7 * r) / 15) : yy;
+    const int j2 = j < 7 ? j + 1 : 7;
+#pragma unroll 1
+    for (int p = 0; p < 8; p++) {
+        float c[2];
+        if (!L::UPS) {
+            c[0] = t.cchunk(m, 0, 2 * yy + (p >> 2))[p & 3];
+            c[1] = t.cchunk(m, 1, 2 * yy + (p >> 2))[p & 3];
+        } else {
+            const int a = 8 * hx + p;
+            const int i = (L::HMAX == 2) ? ((a == 15) ? 6 : (7 * a) / 15) : p;
+            const int i2 = i < 7 ? i + 1 : 7;
+            const float4 w = t.w[r * kWStride + a];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const float p00 = t.cchunk(m, k, 2 * j + (i >> 2))[i & 3], p10 = t.cchunk(m, k, 2 * j + (i2 >> 2))[i2 & 3];
+                const float p01 = t.cchunk(m, k, 2 * j2 + (i >> 2))[i & 3], p11 = t.cchunk(m, k, 2 * j2 + (i2 >> 2))[i2 & 3];
+                const float n = fmaf(w.w, p11, fmaf(w.z, p01, fmaf(w.y, p10, w.x * p00)));  // integers: exact in any order
+                c[k] = fmaf(n, 1.0f / 15.0f, BJ_MAGIC) - BJ_MAGIC;
+            }
+        }
+        const uint32_t rgb = ycc_to_rgb_exact_packed((int)yrow[p], c[0], c[1]);
+        stage[3 * p] = (unsigned char)rgb;
+        stage[3 * p + 1] = (unsigned char)(rgb >> 8);
+        stage[3 * p + 2] = (unsigned char)(rgb >> 16);
+    }
+}
 
 // One 8-pixel run: pixel row r (0..MCU_H-1) of MCU m (warp-local), horizontal half HX.
 template <class L, int HX>
@@ -225,9 +265,9 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, uint3
         rgb[p] = R | (G << 8) | (B << 16);
     }
     if (btie || guard >= BJ_CHROMA_GUARD || dgmax > 0.5f - BJ_G_ERR) {
-#pragma unroll 1
-        for (int p = 0; p < 8; p++) rgb[p] = ycc_to_rgb_exact_packed(Y[p], cbm[p] + 128.0f, crm[p] + 128.0f);
+        pixel_run_exact<L>(t, m, r, HX);
         if (stats) atomicAdd(&stats[1], 8u);
+        return;
     }
     // 8 pixels x 3 bytes = 6 words
     uint32_t o[6];
@@ -393,14 +433,18 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
         }
     } else if (aligned) {
         const int nvec = nbytes >> 4, tail = nbytes & 15;
+#pragma unroll 1
         for (int r = 0; r < rows; r++) {
+#pragma unroll 1
             for (int v = lane; v < nvec; v += 32)
                 __stcs(reinterpret_cast<uint4*>(gout + (int64_t)r * im.out_pitch + (v << 4)),
                        *reinterpret_cast<const uint4*>(t.a + r * L::ROW_BYTES + (v << 4)));
             if (lane < tail) gout[(int64_t)r * im.out_pitch + (nvec << 4) + lane] = t.a[r * L::ROW_BYTES + (nvec << 4) + lane];
         }
     } else {
+#pragma unroll 1
         for (int r = 0; r < rows; r++)
+#pragma unroll 1
             for (int b = lane; b < nbytes; b += 32) gout[(int64_t)r * im.out_pitch + b] = t.a[r * L::ROW_BYTES + b];
     }
 }

@@ -1,5 +1,5 @@
 import sys, json
-for l in sys.stdin:
+for l in (open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin):
     if l.startswith("{"):
         d = json.loads(l)
         print("value %.0f MP/s  %.2f ms/step | e2e %.0f MP/s %.2f ms" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"]))
