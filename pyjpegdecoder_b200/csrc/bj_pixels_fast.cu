@@ -185,8 +185,10 @@ __device__ __noinline__ void pixel_run_exact(const Tiles<L>& t, int m, int r, in
 }
 
 // One 8-pixel run: pixel row r (0..MCU_H-1) of MCU m (warp-local), horizontal half HX.
+// `wide` (warp-level knowledge from phase A): some sample of this MCU may lie outside the range in which the
+// fp32 colour offsets are proven exact (|Cb-128| >= 125: B can tie; |Cr-128| >= 250; |Y| huge) -> exact path.
 template <class L, int HX>
-__device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, uint32_t* stats) {
+__device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, bool wide, uint32_t* stats) {
     const int ys = (r >> 3) * L::HMAX + HX, yy = r & 7;
     const uint4 yv = *reinterpret_cast<const uint4*>(t.yrow(m, ys, yy));
     const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
@@ -248,23 +250,22 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, uint3
     }
     // colour: offsets from chroma in fp32, integer add + clamp; see bj_pixel_math.cuh for the tie rules
     uint32_t rgb[8];
-    float guard = 0.f, dgmax = 0.f;
-    bool btie = false;
+    float dgmax = 0.f;
 #pragma unroll
     for (int p = 0; p < 8; p++) {
         const float cb = cbm[p], cr = crm[p];
-        float rC = 1.402f * cr, gC = fmaf(-0.71414f, cr, -0.34414f * cb), bC = 1.772f * cb;
-        float wr = rC + BJ_MAGIC, wg = gC + BJ_MAGIC, wb = bC + BJ_MAGIC;
+        // offset + 1.5 * 2^23 in one rounding: the low mantissa bits are round-to-nearest(offset)
+        const float wr = fmaf(1.402f, cr, BJ_MAGIC), wb = fmaf(1.772f, cb, BJ_MAGIC);
+        const float gC = fmaf(-0.71414f, cr, -0.34414f * cb);
+        const float wg = gC + BJ_MAGIC;
         dgmax = fmaxf(dgmax, fabsf(gC - (wg - BJ_MAGIC)));
-        guard = fmaxf(guard, fmaxf(fabsf(cb), fabsf(cr)));
-        btie = btie || (fabsf(cb) == 125.0f);
         const int yb = Y[p] - BJ_MAGIC_BITS;
         uint32_t R = (uint32_t)__viaddmin_s32_relu(__float_as_int(wr), yb, 255);
         uint32_t G = (uint32_t)__viaddmin_s32_relu(__float_as_int(wg), yb, 255);
         uint32_t B = (uint32_t)__viaddmin_s32_relu(__float_as_int(wb), yb, 255);
         rgb[p] = R | (G << 8) | (B << 16);
     }
-    if (btie || guard >= BJ_CHROMA_GUARD || dgmax > 0.5f - BJ_G_ERR) {
+    if (wide || dgmax > 0.5f - BJ_G_ERR) {
         pixel_run_exact<L>(t, m, r, HX);
         if (stats) atomicAdd(&stats[1], 8u);
         return;
@@ -339,10 +340,11 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
     if (M <= 0) return;
 
     // ---- phase A: one lane per block ---------------------------------------------------------------
+    unsigned wide_mask;  // blocks whose samples may leave the range the fast colour path is proven for
     {
         const int blk = lane;
         const int m = blk / L::BPM, slot = blk - m * L::BPM;
-        bool flagged = false;
+        bool flagged = false, wide_blk = false;
         if (blk < nblk) {
             const int comp = slot < L::NY ? 0 : slot - L::NY + 1;
             float f[64];
@@ -362,7 +364,8 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
                     if (c * 8 + e) S += fabsf(x);
                 }
             }
-            const float T = fmaf(S, BJ_IDCT_ERR_REL, fmaf(fabsf(f[0]), BJ_IDCT_ERR_DC, BJ_IDCT_ERR_ABS));
+            const float dc_abs = fabsf(f[0]);
+            const float T = fmaf(S, BJ_IDCT_ERR_REL, fmaf(dc_abs, BJ_IDCT_ERR_DC, BJ_IDCT_ERR_ABS));
             bj::idct8x8_fast(f);
             float maxd = 0.f;
 #pragma unroll
@@ -390,7 +393,11 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
                 }
             }
             flagged = maxd > 0.5f - T;
+            // |sample - 128| <= |DC| / 8 + sum|AC| / 4 + 1/2 (every basis value is at most 1/8 resp. 1/4)
+            const float bound = fmaf(0.25f, S, fmaf(0.125f, dc_abs, 0.5f));
+            wide_blk = bound >= (comp == 0 ? 30000.0f : comp == 1 ? 125.0f : BJ_CHROMA_GUARD);
         }
+        wide_mask = __ballot_sync(0xffffffffu, wide_blk);
         unsigned mask = __ballot_sync(0xffffffffu, flagged);
         __syncwarp();
         if (mask) {
@@ -414,8 +421,9 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
         const int q = q0 + lane;
         const int m = q / L::MCU_H, r = q - m * L::MCU_H;
         if (q < npairs && r < rows) {
-            pixel_run<L, 0>(t, m, r, stats);
-            if (L::HMAX == 2) pixel_run<L, (L::HMAX == 2 ? 1 : 0)>(t, m, r, stats);
+            const bool wide = ((wide_mask >> (m * L::BPM)) & ((1u << L::BPM) - 1u)) != 0u;
+            pixel_run<L, 0>(t, m, r, wide, stats);
+            if (L::HMAX == 2) pixel_run<L, (L::HMAX == 2 ? 1 : 0)>(t, m, r, wide, stats);
         }
     }
     __syncwarp();
