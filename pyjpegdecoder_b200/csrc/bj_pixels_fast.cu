@@ -192,11 +192,11 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, bool 
     const int ys = (r >> 3) * L::HMAX + HX, yy = r & 7;
     const uint4 yv = *reinterpret_cast<const uint4*>(t.yrow(m, ys, yy));
     const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
-    int Y[8];
-#pragma unroll
-    for (int p = 0; p < 8; p++) Y[p] = (int)(int16_t)(yw[p >> 1] >> (16 * (p & 1)));
     unsigned char* stage = t.a + r * L::ROW_BYTES + (m * L::MCU_W + 8 * HX) * L::CH;
     if (L::NCOMP == 1) {
+        int Y[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) Y[p] = (int)(int16_t)(yw[p >> 1] >> (16 * (p & 1)));
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int p = 0; p < 4; p++) {
@@ -249,35 +249,44 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, bool 
         }
     }
     // colour: offsets from chroma in fp32, integer add + clamp; see bj_pixel_math.cuh for the tie rules
-    uint32_t rgb[8];
+    // Two pixels per instruction: the low halves of the magic-biased offsets are round(offset) as int16 (the
+    // bias 0x4B400000 has a zero low half), luma is already a packed int16 pair, and one DPX
+    // add-min-relu (VIADDMNMX.S16x2) gives clamp(Y + round(offset), 0, 255) for both.  |Y + offset| stays far
+    // below 2^15 because `wide` MCUs (huge samples) never get here.
+    uint32_t rg[4], bb[4];  // per pixel pair: bytes (R0, G0, R1, G1) and halves (B0, B1)
     float dgmax = 0.f;
 #pragma unroll
-    for (int p = 0; p < 8; p++) {
-        const float cb = cbm[p], cr = crm[p];
-        // offset + 1.5 * 2^23 in one rounding: the low mantissa bits are round-to-nearest(offset)
-        const float wr = fmaf(1.402f, cr, BJ_MAGIC), wb = fmaf(1.772f, cb, BJ_MAGIC);
-        const float gC = fmaf(-0.71414f, cr, -0.34414f * cb);
-        const float wg = gC + BJ_MAGIC;
-        dgmax = fmaxf(dgmax, fabsf(gC - (wg - BJ_MAGIC)));
-        const int yb = Y[p] - BJ_MAGIC_BITS;
-        uint32_t R = (uint32_t)__viaddmin_s32_relu(__float_as_int(wr), yb, 255);
-        uint32_t G = (uint32_t)__viaddmin_s32_relu(__float_as_int(wg), yb, 255);
-        uint32_t B = (uint32_t)__viaddmin_s32_relu(__float_as_int(wb), yb, 255);
-        rgb[p] = R | (G << 8) | (B << 16);
+    for (int k = 0; k < 4; k++) {
+        float wr[2], wg[2], wb[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const float cb = cbm[2 * k + h], cr = crm[2 * k + h];
+            // offset + 1.5 * 2^23 in one rounding: the low mantissa bits are round-to-nearest(offset)
+            wr[h] = fmaf(1.402f, cr, BJ_MAGIC);
+            wb[h] = fmaf(1.772f, cb, BJ_MAGIC);
+            const float gC = fmaf(-0.71414f, cr, -0.34414f * cb);
+            wg[h] = gC + BJ_MAGIC;
+            dgmax = fmaxf(dgmax, fabsf(gC - (wg[h] - BJ_MAGIC)));
+        }
+        const uint32_t RR = __viaddmin_s16x2_relu(__byte_perm(__float_as_uint(wr[0]), __float_as_uint(wr[1]), 0x5410), yw[k], 0x00FF00FFu);
+        const uint32_t GG = __viaddmin_s16x2_relu(__byte_perm(__float_as_uint(wg[0]), __float_as_uint(wg[1]), 0x5410), yw[k], 0x00FF00FFu);
+        bb[k] = __viaddmin_s16x2_relu(__byte_perm(__float_as_uint(wb[0]), __float_as_uint(wb[1]), 0x5410), yw[k], 0x00FF00FFu);
+        rg[k] = __byte_perm(RR, GG, 0x6240);
     }
     if (wide || dgmax > 0.5f - BJ_G_ERR) {
         pixel_run_exact<L>(t, m, r, HX);
         if (stats) atomicAdd(&stats[1], 8u);
         return;
     }
-    // 8 pixels x 3 bytes = 6 words
+    // 8 pixels x 3 bytes = 6 words: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3 | ...
     uint32_t o[6];
-    o[0] = rgb[0] | (rgb[1] << 24);
-    o[1] = (rgb[1] >> 8) | (rgb[2] << 16);
-    o[2] = (rgb[2] >> 16) | (rgb[3] << 8);
-    o[3] = rgb[4] | (rgb[5] << 24);
-    o[4] = (rgb[5] >> 8) | (rgb[6] << 16);
-    o[5] = (rgb[6] >> 16) | (rgb[7] << 8);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const uint32_t t0 = rg[2 * q], t1 = rg[2 * q + 1], b0 = bb[2 * q], b1 = bb[2 * q + 1];
+        o[3 * q] = __byte_perm(t0, b0, 0x2410);                             // R0 G0 B0 R1
+        o[3 * q + 1] = __byte_perm(__byte_perm(t0, b0, 0x0063), t1, 0x5410);  // G1 B1 | R2 G2
+        o[3 * q + 2] = __byte_perm(t1, b1, 0x6324);                         // B2 R3 G3 B3
+    }
     uint2* s2 = reinterpret_cast<uint2*>(stage);
     s2[0] = make_uint2(o[0], o[1]);
     s2[1] = make_uint2(o[2], o[3]);
