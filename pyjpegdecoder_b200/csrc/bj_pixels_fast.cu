@@ -376,6 +376,8 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
             const float dc_abs = fabsf(f[0]);
             const float T = fmaf(S, BJ_IDCT_ERR_REL, fmaf(dc_abs, BJ_IDCT_ERR_DC, BJ_IDCT_ERR_ABS));
             bj::idct8x8_fast(f);
+            // round + level shift in one add: the low mantissa bits of v + (1.5 * 2^23 + 128) are rint(v) + 128
+            constexpr float kMagicShift = BJ_MAGIC + 128.0f;
             float maxd = 0.f;
 #pragma unroll
             for (int y = 0; y < 8; y++) {
@@ -383,22 +385,22 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
 #pragma unroll
                 for (int x = 0; x < 8; x++) {
                     float v = f[y * 8 + x];
-                    w[x] = v + BJ_MAGIC;
-                    maxd = fmaxf(maxd, fabsf(v - (w[x] - BJ_MAGIC)));
+                    w[x] = v + kMagicShift;
+                    maxd = fmaxf(maxd, fabsf(v - (w[x] - kMagicShift)));
                 }
                 if (comp == 0) {
-                    uint32_t iv[8];
-#pragma unroll
-                    for (int x = 0; x < 8; x++) iv[x] = (uint32_t)(__float_as_int(w[x]) - BJ_MAGIC_BITS + 128);
+                    // int16 pairs = the low halves of the biased floats (the bias has a zero low half)
                     *reinterpret_cast<uint4*>(t.yrow(m, slot, y)) =
-                        make_uint4(__byte_perm(iv[0], iv[1], 0x5410), __byte_perm(iv[2], iv[3], 0x5410),
-                                   __byte_perm(iv[4], iv[5], 0x5410), __byte_perm(iv[6], iv[7], 0x5410));
+                        make_uint4(__byte_perm(__float_as_uint(w[0]), __float_as_uint(w[1]), 0x5410),
+                                   __byte_perm(__float_as_uint(w[2]), __float_as_uint(w[3]), 0x5410),
+                                   __byte_perm(__float_as_uint(w[4]), __float_as_uint(w[5]), 0x5410),
+                                   __byte_perm(__float_as_uint(w[6]), __float_as_uint(w[7]), 0x5410));
                 } else {
-                    // rint(v) + 128 = w - (MAGIC - 128), exact
+                    // rint(v) + 128 = w - MAGIC, exact
                     *reinterpret_cast<float4*>(t.cchunk(m, comp - 1, 2 * y)) =
-                        make_float4(w[0] - (BJ_MAGIC - 128.f), w[1] - (BJ_MAGIC - 128.f), w[2] - (BJ_MAGIC - 128.f), w[3] - (BJ_MAGIC - 128.f));
+                        make_float4(w[0] - BJ_MAGIC, w[1] - BJ_MAGIC, w[2] - BJ_MAGIC, w[3] - BJ_MAGIC);
                     *reinterpret_cast<float4*>(t.cchunk(m, comp - 1, 2 * y + 1)) =
-                        make_float4(w[4] - (BJ_MAGIC - 128.f), w[5] - (BJ_MAGIC - 128.f), w[6] - (BJ_MAGIC - 128.f), w[7] - (BJ_MAGIC - 128.f));
+                        make_float4(w[4] - BJ_MAGIC, w[5] - BJ_MAGIC, w[6] - BJ_MAGIC, w[7] - BJ_MAGIC);
                 }
             }
             flagged = maxd > 0.5f - T;
