@@ -168,7 +168,11 @@ __device__ __noinline__ void pixel_run_exact(const Tiles<L>& t, int m, int r, in
             const int a = 8 * hx + p;
             const int i = (L::HMAX == 2) ? ((a == 15) ? 6 : (7 * a) / 15) : p;
             const int i2 = i < 7 ? i + 1 : 7;
-            const float4 w = t.w[r * kWStride + a];
+            float4 w = t.w[r * kWStride + a];
+            if (L::HMAX == 2 && hx) {  // right half: stored right-to-left with the taps swapped (see pixel_run)
+                const float4 e = t.w[r * kWStride + 23 - a];
+                w = make_float4(e.y, e.x, e.w, e.z);
+            }
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const float p00 = t.cchunk(m, k, 2 * j + (i >> 2))[i & 3], p10 = t.cchunk(m, k, 2 * j + (i2 >> 2))[i2 & 3];
@@ -184,15 +188,28 @@ __device__ __noinline__ void pixel_run_exact(const Tiles<L>& t, int m, int r, in
     }
 }
 
-// One 8-pixel run: pixel row r (0..MCU_H-1) of MCU m (warp-local), horizontal half HX.
+// One 8-pixel run: pixel row r (0..MCU_H-1) of MCU m (warp-local), horizontal half hx.
 // `wide` (warp-level knowledge from phase A): some sample of this MCU may lie outside the range in which the
 // fp32 colour offsets are proven exact (|Cb-128| >= 125: B can tie; |Cr-128| >= 250; |Y| huge) -> exact path.
-template <class L, int HX>
-__device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, bool wide, uint32_t* stats) {
-    const int ys = (r >> 3) * L::HMAX + HX, yy = r & 7;
+// For layouts with two luma blocks per MCU row (HMAX == 2) the half `hx` is a RUN-TIME value, so that one lane
+// can take one run and the (MCU, row, half) triples fill the warp exactly (4:2:0: 160 runs = 5 x 32 lanes; with a
+// lane per (MCU, row) doing both halves in turn it was 80 pairs on 96 lane slots).  One code body serves both
+// halves because the right half is the mirror image of the left one: output column a = 15 - a' reads source
+// cells 6 - i(a'), so the right half walks its pixels right-to-left over the mirrored chroma columns with the
+// left half's compile-time tap indices; the weight table holds the right half's entries mirrored and with the
+// left/right taps swapped, and luma pairs / RGB pairs are flipped with one byte-permute each.
+template <class L>
+__device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int hx, bool wide, uint32_t* stats) {
+    const int ys = (r >> 3) * L::HMAX + hx, yy = r & 7;
     const uint4 yv = *reinterpret_cast<const uint4*>(t.yrow(m, ys, yy));
-    const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
-    unsigned char* stage = t.a + r * L::ROW_BYTES + (m * L::MCU_W + 8 * HX) * L::CH;
+    const uint32_t flip = (L::HMAX == 2 && hx) ? 0x5476u : 0x3210u;  // byte-permute selector: second operand, halves swapped
+    uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+    if (L::HMAX == 2) {
+        const uint32_t y0 = __byte_perm(yv.x, yv.w, flip), y1 = __byte_perm(yv.y, yv.z, flip);
+        const uint32_t y2 = __byte_perm(yv.z, yv.y, flip), y3 = __byte_perm(yv.w, yv.x, flip);
+        yw[0] = y0; yw[1] = y1; yw[2] = y2; yw[3] = y3;
+    }
+    unsigned char* stage = t.a + r * L::ROW_BYTES + (m * L::MCU_W + 8 * hx) * L::CH;
     if (L::NCOMP == 1) {
         int Y[8];
 #pragma unroll
@@ -220,32 +237,53 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, bool 
     } else {
         int j = (L::VMAX == 2) ? ((r == 15) ? 6 : (7 * r) / 15) : r;
         int j2 = j < 7 ? j + 1 : 7;
-        const float4* w = t.w + r * kWStride + 8 * HX;
+        const float4* w = t.w + r * kWStride + 8 * hx;
         float4 ww[8];
 #pragma unroll
         for (int p = 0; p < 8; p++) ww[p] = w[p];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            float p0[8], p1[8];
-            {
-                float4 a0 = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j));
-                float4 a1 = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j + 1));
-                float4 b0 = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j2));
-                float4 b1 = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j2 + 1));
-                p0[0] = a0.x; p0[1] = a0.y; p0[2] = a0.z; p0[3] = a0.w; p0[4] = a1.x; p0[5] = a1.y; p0[6] = a1.z; p0[7] = a1.w;
-                p1[0] = b0.x; p1[1] = b0.y; p1[2] = b0.z; p1[3] = b0.w; p1[4] = b1.x; p1[5] = b1.y; p1[6] = b1.z; p1[7] = b1.w;
-            }
             float* o = k ? crm : cbm;
+            if (L::HMAX == 2) {
+                // window of five source columns: 0..4 for the left half, 7..3 (mirrored) for the right half
+                float p0[5], p1[5];
+                {
+                    const float4 a = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j + hx));
+                    const float4 b = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j2 + hx));
+                    p0[4] = t.cchunk(m, k, 2 * j + 1 - hx)[hx ? 3 : 0];
+                    p1[4] = t.cchunk(m, k, 2 * j2 + 1 - hx)[hx ? 3 : 0];
+                    p0[0] = hx ? a.w : a.x; p0[1] = hx ? a.z : a.y; p0[2] = hx ? a.y : a.z; p0[3] = hx ? a.x : a.w;
+                    p1[0] = hx ? b.w : b.x; p1[1] = hx ? b.z : b.y; p1[2] = hx ? b.y : b.z; p1[3] = hx ? b.x : b.w;
+                }
 #define BJ_PIX(P)                                                                                          \
     {                                                                                                      \
-        constexpr int i = (L::HMAX == 2) ? Cell<8 * HX + P>::i : P;                                        \
-        constexpr int i2 = i < 7 ? i + 1 : 7;                                                              \
-        float n = fmaf(ww[P].w, p1[i2], fmaf(ww[P].z, p1[i], fmaf(ww[P].y, p0[i2], ww[P].x * p0[i])));     \
+        constexpr int i = Cell<P>::i;                                                                      \
+        float n = fmaf(ww[P].w, p1[i + 1], fmaf(ww[P].z, p1[i], fmaf(ww[P].y, p0[i + 1], ww[P].x * p0[i]))); \
         /* N/15 rounded (never a tie), minus 128: both subtractions folded into one exact fp32 add */      \
         o[P] = fmaf(n, 1.0f / 15.0f, BJ_MAGIC) - (BJ_MAGIC + 128.0f);                                      \
     }
-            BJ_PIX(0) BJ_PIX(1) BJ_PIX(2) BJ_PIX(3) BJ_PIX(4) BJ_PIX(5) BJ_PIX(6) BJ_PIX(7)
+                BJ_PIX(0) BJ_PIX(1) BJ_PIX(2) BJ_PIX(3) BJ_PIX(4) BJ_PIX(5) BJ_PIX(6) BJ_PIX(7)
 #undef BJ_PIX
+            } else {
+                float p0[8], p1[8];
+                {
+                    float4 a0 = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j));
+                    float4 a1 = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j + 1));
+                    float4 b0 = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j2));
+                    float4 b1 = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j2 + 1));
+                    p0[0] = a0.x; p0[1] = a0.y; p0[2] = a0.z; p0[3] = a0.w; p0[4] = a1.x; p0[5] = a1.y; p0[6] = a1.z; p0[7] = a1.w;
+                    p1[0] = b0.x; p1[1] = b0.y; p1[2] = b0.z; p1[3] = b0.w; p1[4] = b1.x; p1[5] = b1.y; p1[6] = b1.z; p1[7] = b1.w;
+                }
+#define BJ_PIX(P)                                                                                          \
+    {                                                                                                      \
+        constexpr int i = P;                                                                               \
+        constexpr int i2 = i < 7 ? i + 1 : 7;                                                              \
+        float n = fmaf(ww[P].w, p1[i2], fmaf(ww[P].z, p1[i], fmaf(ww[P].y, p0[i2], ww[P].x * p0[i])));     \
+        o[P] = fmaf(n, 1.0f / 15.0f, BJ_MAGIC) - (BJ_MAGIC + 128.0f);                                      \
+    }
+                BJ_PIX(0) BJ_PIX(1) BJ_PIX(2) BJ_PIX(3) BJ_PIX(4) BJ_PIX(5) BJ_PIX(6) BJ_PIX(7)
+#undef BJ_PIX
+            }
         }
     }
     // colour: offsets from chroma in fp32, integer add + clamp; see bj_pixel_math.cuh for the tie rules
@@ -274,9 +312,17 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, bool 
         rg[k] = __byte_perm(RR, GG, 0x6240);
     }
     if (wide || dgmax > 0.5f - BJ_G_ERR) {
-        pixel_run_exact<L>(t, m, r, HX);
+        pixel_run_exact<L>(t, m, r, hx);
         if (stats) atomicAdd(&stats[1], 8u);
         return;
+    }
+    if (L::HMAX == 2) {  // back to left-to-right order
+        const uint32_t r0 = __byte_perm(rg[0], rg[3], flip), r1 = __byte_perm(rg[1], rg[2], flip);
+        const uint32_t r2 = __byte_perm(rg[2], rg[1], flip), r3 = __byte_perm(rg[3], rg[0], flip);
+        const uint32_t b0 = __byte_perm(bb[0], bb[3], flip), b1 = __byte_perm(bb[1], bb[2], flip);
+        const uint32_t b2 = __byte_perm(bb[2], bb[1], flip), b3 = __byte_perm(bb[3], bb[0], flip);
+        rg[0] = r0; rg[1] = r1; rg[2] = r2; rg[3] = r3;
+        bb[0] = b0; bb[1] = b1; bb[2] = b2; bb[3] = b3;
     }
     // 8 pixels x 3 bytes = 6 words: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3 | ...
     uint32_t o[6];
@@ -317,13 +363,18 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
     for (int i = tid; i < NCOMP * 64; i += kThreads) qt[i] = qtabs[(size_t)im.qtab[i >> 6] * 64 + (i & 63)];
     if (L::UPS) {
         for (int i = tid; i < 256; i += kThreads) {
-            int b = i >> 4, a = i & 15;
+            // entry a' of row b: a' < 8 -> output column a'; a' >= 8 (right half, HMAX == 2) -> column 23 - a',
+            // i.e. the right half stored right-to-left, with the left/right taps swapped (see pixel_run)
+            const int b = i >> 4, ap = i & 15;
+            const bool mirror = (HMAX == 2) && ap >= 8;
+            const int a = mirror ? 23 - ap : ap;
             int ii = a & 7, s = 0, jj = b & 7, tt = 0;
             if (HMAX == 2) bj::up_cell(a, ii, s);
             if (VMAX == 2) bj::up_cell(b, jj, tt);
             int w00, w10, w01, w11;
             bj::up_weights_2d(ii, jj, s, tt, w00, w10, w01, w11);
-            wtab[b * kWStride + a] = make_float4((float)w00, (float)w10, (float)w01, (float)w11);
+            wtab[b * kWStride + ap] = mirror ? make_float4((float)w10, (float)w00, (float)w11, (float)w01)
+                                             : make_float4((float)w00, (float)w10, (float)w01, (float)w11);
         }
     }
     // ---- this warp's tile ----------------------------------------------------------------------------
@@ -426,15 +477,15 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
     const int x0 = m0 * L::MCU_W, y0 = my * L::MCU_H;
     const int cols = min(M * L::MCU_W, (int)im.width - x0);
     const int rows = min(L::MCU_H, (int)im.height - y0);
-    const int npairs = M * L::MCU_H;
+    const int nunits = M * L::MCU_H * L::HMAX;  // 8-pixel runs: (MCU, half, row)
 #pragma unroll 1
-    for (int q0 = 0; q0 < npairs; q0 += 32) {
-        const int q = q0 + lane;
-        const int m = q / L::MCU_H, r = q - m * L::MCU_H;
-        if (q < npairs && r < rows) {
+    for (int u0 = 0; u0 < nunits; u0 += 32) {
+        const int u = u0 + lane;
+        const int r = u % L::MCU_H, mh = u / L::MCU_H;
+        const int hx = mh % L::HMAX, m = mh / L::HMAX;
+        if (u < nunits && r < rows) {
             const bool wide = ((wide_mask >> (m * L::BPM)) & ((1u << L::BPM) - 1u)) != 0u;
-            pixel_run<L, 0>(t, m, r, wide, stats);
-            if (L::HMAX == 2) pixel_run<L, (L::HMAX == 2 ? 1 : 0)>(t, m, r, wide, stats);
+            pixel_run<L>(t, m, r, hx, wide, stats);
         }
     }
     __syncwarp();
