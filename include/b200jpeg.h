@@ -249,6 +249,10 @@ int bj_host_walk(const uint8_t* data, uint64_t n, bj_host_entry* entries, int ma
 void bj_host_walk_batch(const uint8_t* raw, const uint64_t* off, const uint64_t* size, int n_files,
                         bj_host_entry* entries, int max_entries, int32_t* counts, int n_threads);
 
+/* Threaded gather of n_files host buffers into one packed buffer: memcpy(dst + off[i], src[i], size[i]). */
+void bj_host_pack(const uint8_t* const* src, const uint64_t* size, const uint64_t* off, int n_files, uint8_t* dst,
+                  int n_threads);
+
 /*
  * Pixel stages.  Replaces, for a whole batch of images in one launch:
  *   undo_zigzag * Q              jpeg_decoder.py:1648-1662, :869, :1347-1348   (int16 product wraps)

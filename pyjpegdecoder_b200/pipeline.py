@@ -11,6 +11,7 @@ torch tensors are used as device buffers only; all compute is in libb200jpeg.so.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -211,9 +212,22 @@ def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot: Optional[in
         buf = pool[:total]
     else:
         buf = torch.empty(total, dtype=torch.uint8, pin_memory=pinned)
-    view = buf.numpy()
-    for d, off in zip(datas, offsets):
-        view[off:off + len(d)] = np.frombuffer(d, dtype=np.uint8)
+    n = len(datas)
+    if n >= 8 and all(type(d) is bytes for d in datas):
+        # threaded gather in C (csrc/bj_host.cu): the pointers come straight from the bytes objects
+        L = _native.lib()
+        if not getattr(L, "_pack_bound", False):
+            L.bj_host_pack.restype = None
+            L.bj_host_pack.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+            L._pack_bound = True
+        ptrs = (ctypes.c_char_p * n)(*datas)
+        sizes = np.fromiter((len(d) for d in datas), dtype=np.uint64, count=n)
+        offs = np.asarray(offsets, dtype=np.uint64)
+        L.bj_host_pack(ptrs, sizes.ctypes.data, offs.ctypes.data, n, buf.data_ptr(), min(16, os.cpu_count() or 1))
+    else:
+        view = buf.numpy()
+        for d, off in zip(datas, offsets):
+            view[off:off + len(d)] = np.frombuffer(d, dtype=np.uint8)
     return buf, offsets
 
 
@@ -261,7 +275,10 @@ class DevicePipeline:
 
     STAGES = ("unstuff", "plan", "spec", "fix", "write", "other_scans", "pixels")
 
-    def __init__(self, plan: BatchPlan, device=None, stream: Optional[torch.cuda.Stream] = None):
+    def __init__(self, plan: BatchPlan, device=None, stream: Optional[torch.cuda.Stream] = None,
+                 raw: Optional[torch.Tensor] = None):
+        """raw: device copy of the packed file bytes, if the caller has already started it (see
+        decode_batch_on_device: the H2D copy runs while the host is still planning)."""
         self.plan = plan
         self.dev = require_cuda(device)
         self.L = _bind()
@@ -274,7 +291,9 @@ class DevicePipeline:
                 self.tile_scan = to_device(plan.tile_scan, dev)
                 self.lut = torch.from_numpy(plan.lut.view(np.int32)).to(dev)
                 self.dg = DeviceGeometry(g, dev)
-                self.raw = torch.empty(plan.raw_bytes, dtype=torch.uint8, device=dev)
+                self.raw = raw if raw is not None else torch.empty(plan.raw_bytes, dtype=torch.uint8, device=dev)
+                if self.raw.numel() != plan.raw_bytes or not self.raw.is_cuda:
+                    raise ValueError("raw: wrong size or not a device tensor")
                 self.words_len = plan.raw_bytes // 4 + 64
                 self.words = torch.empty(self.words_len, dtype=torch.int32, device=dev)
                 self.tile_sum = torch.empty(plan.n_tiles + 1, dtype=torch.int64, device=dev)
@@ -392,6 +411,13 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
     if packed is None:
         packed = pack_files(datas, reuse_slot=0 if check else None)
     raw_host, offsets = packed
+    # start the host->device copy of the file bytes now: it overlaps the host-side planning below
+    dev = require_cuda(device)
+    with torch.cuda.device(dev):
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st):
+            raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=dev)
+            raw_dev.copy_(raw_host, non_blocking=True)
     if plan is None:
         if parsed is None and datas is not None and len(datas) >= FAST_PLAN_MIN_FILES:
             from .fastplan import plan_batch
@@ -400,8 +426,7 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
             if parsed is None:
                 parsed = [parse_jpeg(d) for d in datas]
             plan = BatchPlan(parsed, offsets, raw_host.numel())
-    pipe = DevicePipeline(plan, device, stream)
-    pipe.upload(raw_host)
+    pipe = DevicePipeline(plan, device, stream, raw=raw_dev)
     pipe.launch(out_kind=out_kind, upto_group=upto_wave)
     res = pipe.result()
     if check:

@@ -239,4 +239,47 @@ void hs_dcrefine_stream(const uint32_t* words, uint64_t start_byte, uint32_t nbl
         coef[(size_t)b * 64] = (int16_t)(coef[(size_t)b * 64] | (int16_t)(v << al));
     }
 }
+// EXPERIMENT SUPPORT (test-only): how far does a decoder that starts at a subsequence boundary with the
+// default state (z0, slot 0) have to go before it falls into step with the true decode?  hist[k] counts
+// subsequences whose distance is in [k*64, (k+1)*64) bits (last bin: never within `limit` bits).
+void hs_sync_distance(const uint32_t* words, uint64_t n_words, uint64_t start_byte, uint64_t end_byte,
+                      const SimScan* ss_, int sub_bits, uint32_t limit, uint32_t* hist, int nbins) {
+    const SimScan& sc = *ss_;
+    if (sc.mode != BJ_MODE_BASELINE) return;
+    ScanCtx c = make_ctx(sc);
+    HostSrc src{words, n_words};
+    const uint64_t b0 = start_byte * 8, b1 = end_byte * 8;
+    const uint32_t nbits = (uint32_t)(b1 - b0);
+    std::vector<uint16_t> truth(nbits + 64, 0xFFFF);  // per bit position: z | slot << 7 at a true symbol start
+    {
+        BitReader<HostSrc> rd;
+        rd.seek(&src, b0, 0);
+        int z = 0, slot = 0;
+        SubCount k{0, {0, 0, 0}};
+        while (rd.rel < nbits) {
+            truth[rd.rel] = (uint16_t)(z | (slot << 7));
+            uint32_t before = rd.rel;
+            sync_run<BJ_M_BASE>(rd, z, slot, c, sc.lut, 0xFFFFFFFFu, rd.rel + 1, nbits, k);
+            if (rd.rel == before) break;
+        }
+    }
+    const uint32_t nsub = (nbits + sub_bits - 1) / sub_bits;
+    for (uint32_t l = 1; l < nsub; l++) {
+        const uint32_t own = l * (uint32_t)sub_bits;
+        BitReader<HostSrc> rd;
+        rd.seek(&src, b0, own);
+        int z = 0, slot = 0;
+        SubCount k{0, {0, 0, 0}};
+        uint32_t d = limit;
+        while (rd.rel < nbits && rd.rel - own < limit) {
+            if (truth[rd.rel] == (uint16_t)(z | (slot << 7))) { d = rd.rel - own; break; }
+            uint32_t before = rd.rel;
+            sync_run<BJ_M_BASE>(rd, z, slot, c, sc.lut, 0xFFFFFFFFu, rd.rel + 1, nbits, k);
+            if (rd.rel == before) break;
+        }
+        int bin = (int)(d / 64);
+        if (bin >= nbins) bin = nbins - 1;
+        hist[bin]++;
+    }
+}
 }
