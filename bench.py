@@ -318,8 +318,8 @@ def main():
             stages[k] = {"ms": ms, "share_of_step": ms / sum(stage_ms.values())}
     dom = max((k for k in stages if "gbs" in stages[k]), key=lambda k: stages[k]["ms"])
     # dram__bytes_read.sum + dram__bytes_write.sum per image from the ncu --set full captures under profiles/
-    # (r1b, 64 images per launch): measured DRAM traffic, scaled to the images one launch of this run covers
-    ncu_traffic_per_image = {"pixels": (401.201920e6 + 363.742976e6) / 64, "write": (32.204544e6 + 349.324032e6) / 64,
+    # (r1g, 64 images per launch): measured DRAM traffic, scaled to the images one launch of this run covers
+    ncu_traffic_per_image = {"pixels": (401.185024e6 + 352.591872e6) / 64, "write": (31.839744e6 + 348.748544e6) / 64,
                              "spec": 24.421376e6 / 64, "fix": (19.857408e6 + 3.593472e6) / 64,
                              "unstuff": (24.596224e6 + 24.657920e6) / 64}
     img_per_launch = n_img / n_chunks
@@ -331,7 +331,7 @@ def main():
         tr = ncu_traffic_per_image.get(k)
         return {"kernel": names[k], "bound": "hbm", "achieved": st.get("gbs"), "peak": peak, "unit": "GB/s",
                 "frac": st.get("frac_of_peak"), "traffic": (tr * img_per_launch) if tr else None,
-                "traffic_source": "ncu --set full capture profiles/r1_final_full_summary.csv (64 images), scaled per image",
+                "traffic_source": "ncu --set full capture profiles/r1g_full_summary.csv (64 images), scaled per image",
                 "peak_source": peak_src, "launches_per_step": n_chunks,
                 "algorithmic_bytes_per_launch": alg[k] / n_chunks, "ms_per_launch": st.get("ms", 0.0) / n_chunks,
                 "share_of_step": st.get("share_of_step")}

@@ -22,7 +22,10 @@ def dense_progressive(w=4160, h=2340, quality=90, seed=7, **kw):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    data = dense_progressive()
+    if len(sys.argv) > 2 and sys.argv[2] == "base":   # the reference's own 4160x2340 progressive test image
+        data = (ROOT / "tests/golden/base_image.jpg").read_bytes()
+    else:
+        data = dense_progressive()
     for _ in range(n):
         decode_batch_on_device([data], device="cuda:0")
     torch.cuda.synchronize()
