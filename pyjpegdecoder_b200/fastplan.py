@@ -28,7 +28,7 @@ from .huffman import build_scan_blob
 from .layout import slot0_of, total_blocks
 from .parser import ParsedJpeg, parse_jpeg
 from .pipeline import ENTROPY_THREADS, MAX_SLOTS, MODES, SCAN_DTYPE, SUBSEQ_BITS, UNSTUFF_TILE, ScanGroup
-from .plan import choose_strip, layout_of
+from .plan import choose_strip, layout_of, scan_levels
 
 ENTRY_DTYPE = np.dtype([("start", "<u8"), ("end", "<u8"), ("marker", "<u4"), ("reserved", "<u4")])
 MAX_ENTRIES = 256
@@ -101,6 +101,7 @@ class _Template:
         self.scan_recs = np.zeros(self.nscan, dtype=SCAN_DTYPE)
         self.blobs = []
         self.modes = np.zeros(self.nscan, dtype=np.int64)
+        self.levels = np.asarray(scan_levels(p), dtype=np.int64)
         self.data_start = np.zeros(self.nscan, dtype=np.int64)
         for k, sc in enumerate(p.scans):
             r = self.scan_recs[k]
@@ -296,13 +297,15 @@ class FastPlan:
         for t, b0_ in zip(templates, t_sbase):
             t_recs[int(b0_):int(b0_) + t.nscan] = t.scan_recs
         t_modes = np.concatenate([t.modes for t in templates])
+        t_levels = np.concatenate([t.levels for t in templates])
         nsc = t_nscan[tid]
         img = np.repeat(np.arange(n, dtype=np.int64), nsc)
         kidx = np.arange(len(img), dtype=np.int64) - np.repeat(run_base, nsc)
         flat_t = t_sbase[tid][img] + kidx
         mode = t_modes[flat_t]
-        order = np.lexsort((img, mode, kidx))      # wave (= scan index), then mode, then image
-        img, kidx, flat_t, mode = img[order], kidx[order], flat_t[order], mode[order]
+        level = t_levels[flat_t]
+        order = np.lexsort((kidx, img, mode, level))      # wave (dependency level), then mode, then image, then scan
+        img, kidx, flat_t, mode, level = img[order], kidx[order], flat_t[order], mode[order], level[order]
         rstart, rend = run_start[order], run_end[order]
         recs = t_recs[flat_t].copy()
         raw_off = offsets[img] + rstart
@@ -343,7 +346,7 @@ class FastPlan:
         # groups: runs of equal (wave, mode)
         self.groups: List[ScanGroup] = []
         if len(recs):
-            change = np.flatnonzero((np.diff(kidx) != 0) | (np.diff(mode) != 0)) + 1
+            change = np.flatnonzero((np.diff(level) != 0) | (np.diff(mode) != 0)) + 1
             bounds = np.concatenate(([0], change, [len(recs)]))
             blocks_scan = recs["n_mcu"].astype(np.int64) * recs["nslots"].astype(np.int64)
             for a, b in zip(bounds[:-1], bounds[1:]):

@@ -23,7 +23,7 @@ from .errors import CorruptedJpeg, NativeLibraryError
 from .huffman import build_scan_blob
 from .layout import slot0_of
 from .parser import ParsedJpeg, Scan, parse_jpeg
-from .plan import BatchGeometry
+from .plan import BatchGeometry, scan_levels
 from .stages import DeviceGeometry, image_views, require_cuda, run_pixels, to_device
 
 SUBSEQ_BITS = 1024
@@ -98,7 +98,7 @@ class BatchPlan:
     """Everything the host must compute for one batch: geometry, scan descriptors grouped into waves,
     tile table, Huffman LUT blob, buffer sizes.  `offsets[i]` is where file i starts in the raw buffer."""
 
-    def __init__(self, parsed: Sequence[ParsedJpeg], offsets: Sequence[int], raw_bytes: int):
+    def __init__(self, parsed: Sequence[ParsedJpeg], offsets: Sequence[int], raw_bytes: int, serial_scans: bool = False):
         self.parsed = list(parsed)
         self.geom = BatchGeometry(self.parsed)
         self.raw_bytes = raw_bytes
@@ -108,22 +108,19 @@ class BatchPlan:
         lut_parts: List[np.ndarray] = []
         lut_cache: Dict[tuple, Tuple[int, int, list, list]] = {}
         lut_size = 0
-        # order: wave by wave (k-th scan of every image), inside a wave grouped by mode
-        order: List[Tuple[int, int, int]] = []  # (wave, mode, image, scan idx)
-        max_waves = max(len(p.scans) for p in self.parsed)
-        for w in range(max_waves):
-            items = [(MODES[p.scans[w].kind], i) for i, p in enumerate(self.parsed) if len(p.scans) > w]
-            items.sort()
-            order.extend((w, m, i) for (m, i) in items)
+        # order: wave by wave (scans of equal dependency level, plan.scan_levels), inside a wave grouped by mode
+        order4 = sorted((lv, MODES[p.scans[k].kind], i, k) for i, p in enumerate(self.parsed)
+                        for k, lv in enumerate(scan_levels(p, serial_scans)))
+        order = [(lv, m, i, k) for (lv, m, i, k) in order4]
         self.groups: List[ScanGroup] = []
         stream0 = 0
         sub0 = 0
         tile0 = 0
         tile_counts = []
         cur_key = None
-        for k, (w, mode, i) in enumerate(order):
+        for k, (w, mode, i, sidx) in enumerate(order):
             p = self.parsed[i]
-            sc: Scan = p.scans[w]
+            sc: Scan = p.scans[sidx]
             rec = self.scans[k]
             raw_off = offsets[i] + sc.data_start
             raw_len = sc.data_end - sc.data_start
@@ -419,13 +416,13 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
             raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=dev)
             raw_dev.copy_(raw_host, non_blocking=True)
     if plan is None:
-        if parsed is None and datas is not None and len(datas) >= FAST_PLAN_MIN_FILES:
+        if parsed is None and datas is not None and len(datas) >= FAST_PLAN_MIN_FILES and upto_wave is None:
             from .fastplan import plan_batch
             plan = plan_batch(raw_host, offsets, [len(d) for d in datas])
         else:
             if parsed is None:
                 parsed = [parse_jpeg(d) for d in datas]
-            plan = BatchPlan(parsed, offsets, raw_host.numel())
+            plan = BatchPlan(parsed, offsets, raw_host.numel(), serial_scans=upto_wave is not None)
     pipe = DevicePipeline(plan, device, stream, raw=raw_dev)
     pipe.launch(out_kind=out_kind, upto_group=upto_wave)
     res = pipe.result()

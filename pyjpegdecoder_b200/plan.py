@@ -31,6 +31,30 @@ def idct_table_t() -> np.ndarray:
     return _IDCT_TABLE_T
 
 
+def scan_levels(p: ParsedJpeg, serial: bool = False) -> List[int]:
+    """Dependency level of every scan of an image: scans of the same level touch disjoint coefficients and can
+    run in the same wave of launches.  A scan depends on every earlier scan that shares a component with it and
+    whose spectral band overlaps its own (DC scans: band {0}); refinement scans additionally wait for every
+    earlier scan of their components whatever the band (their parse looks at whole blocks).
+    A progressive file from libjpeg's default script goes from 10 waves to 5: DC | 4 x AC first | Y refine |
+    DC refine + Cr, Cb, Y refine.  serial=True: one level per scan (per-scan parity tests)."""
+    if serial:
+        return list(range(len(p.scans)))
+    levels: List[int] = []
+    for k, sc in enumerate(p.scans):
+        lv = 0
+        for j in range(k):
+            sj = p.scans[j]
+            if not set(sc.comps) & set(sj.comps):
+                continue
+            overlap = not (sc.se < sj.ss or sj.se < sc.ss)
+            both_ac = sc.ss > 0 and sj.ss > 0
+            if overlap or (both_ac and (sc.kind == "ac_refine" or sj.kind == "ac_refine")):
+                lv = max(lv, levels[j] + 1)
+        levels.append(lv)
+    return levels
+
+
 def layout_of(p: ParsedJpeg) -> int:
     """BJ_LAYOUT_* code: which specialised pixel kernel handles the image (0 = generic)."""
     if p.ncomp == 1:

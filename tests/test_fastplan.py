@@ -67,3 +67,21 @@ def test_fastplan_raises_like_the_parser():
     raw, offs = pack_files([good, b"\x89PNG-not-a-jpeg"], pin=False)
     with pytest.raises(NotJpeg):
         FastPlan(raw.numpy(), offs, [len(good), 15])
+
+
+def test_scan_levels_of_the_default_progressive_script():
+    """libjpeg's default progressive script: 10 scans collapse into 3 dependency levels (5 launch waves)."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    from pyjpegdecoder_b200.plan import scan_levels
+    rng = np.random.default_rng(0)
+    b = io.BytesIO()
+    Image.fromarray(rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)).save(b, "JPEG", progressive=True, subsampling=2)
+    p = parse_jpeg(b.getvalue())
+    kinds = [s.kind for s in p.scans]
+    assert kinds == ["dc_first", "ac_first", "ac_first", "ac_first", "ac_first", "ac_refine", "dc_refine",
+                     "ac_refine", "ac_refine", "ac_refine"]
+    assert scan_levels(p) == [0, 0, 0, 0, 0, 1, 1, 1, 1, 2]
+    assert scan_levels(p, serial=True) == list(range(10))
