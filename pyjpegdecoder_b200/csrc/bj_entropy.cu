@@ -385,54 +385,49 @@ __global__ void __launch_bounds__(T) fix_local_kernel(const bj_scan* __restrict_
     if (changes && B.sync_changes) atomicAdd(B.sync_changes, changes);
 }
 
-// ---- fix-up, stage 2: one warp per scan ------------------------------------------------------------------
+// ---- fix-up, stage 2: one CTA per scan --------------------------------------------------------------------
 // After stage 1 the only places where an entry state can still differ from its predecessor's exit are the
-// CTA boundaries of stage 1 (every T-th subsequence).  Lane 0 walks them in order; on a mismatch it
-// re-decodes forward from the corrected state until the exit state matches the stored entry of the next
-// subsequence (from there on everything is consistent up to the next boundary).  Then the whole warp
-// computes the segmented exclusive prefix sums (first block index and DC predictors per subsequence).
-// Nothing waits on another CTA: all scans of the batch are repaired concurrently, one thread each.
-__global__ void __launch_bounds__(128) chain_kernel(const bj_scan* __restrict__ scans, int scan_first, int n_scans,
-                                                    bj_entropy_buffers B) {
-    __shared__ CtaSharedLite shs[4];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int si_idx = blockIdx.x * 4 + warp;
-    if (si_idx >= n_scans) return;
-    CtaSharedLite& sh = shs[warp];
-    {
-        const uint32_t* srcw = reinterpret_cast<const uint32_t*>(&scans[scan_first + si_idx]);
-        for (int i = lane; i < (int)(sizeof(bj_scan) / 4); i += 32) reinterpret_cast<uint32_t*>(&sh.sc)[i] = srcw[i];
-        __syncwarp();
-        if (lane == 0) {
-            const bj_scan& sc = sh.sc;
-            for (int i = 0; i < BJ_MAX_SLOTS; i++) {
-                sh.ctx.dc_tab[i] = sc.slot_dc[i];
-                sh.ctx.ac_tab[i] = sc.slot_ac[i];
-                sh.ctx.slot_comp[i] = sc.slot_comp[i];
-            }
-            sh.ctx.nslots = sc.nslots;
-            sh.ctx.ss = sc.ss;
-            sh.ctx.se = sc.se;
-            sh.ctx.al = sc.al;
-            uint32_t last = sc.stream0 + sc.n_streams - 1;
-            uint64_t bits = (B.stream_end[last] - B.stream_start[last]) * 8;
-            sh.scan_nsub = B.stream_sub[last] + (uint32_t)((bits + S - 1) / S);
-        }
-        __syncwarp();
-    }
+// CTA boundaries of stage 1 (every T-th subsequence).  Thread i owns boundaries (i + 1) * T + k * kChainThreads
+// * T; on a mismatch it re-decodes forward from the corrected state until the exit state matches the stored
+// entry of the next subsequence, never beyond its own range of T subsequences (so threads never race); a
+// correction that reaches the end of a range is picked up by the owner of the next boundary in the next pass.
+// Passes repeat until nothing mismatches.  Then warp 0 computes the segmented exclusive prefix sums (first block
+// index and DC predictors per subsequence; segments = streams, their heads marked in a shared-memory bitmap).
+// Nothing waits on another CTA: all scans of the batch are repaired concurrently.
+constexpr int kChainThreads = 128;
+
+__global__ void __launch_bounds__(kChainThreads) chain_kernel(const bj_scan* __restrict__ scans, int scan_first, int n_scans,
+                                                              bj_entropy_buffers B, uint32_t bitmap_words, uint32_t lut_cap) {
+    extern __shared__ uint32_t s_heads[];  // bitmap_words words (0: scans with several streams fall back to a binary search)
+    uint32_t* const s_lut = s_heads + bitmap_words;  // lut_cap words: the scan's Huffman LUTs when they fit
+    __shared__ CtaSharedLite sh;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if ((int)blockIdx.x >= n_scans) return;
+    load_scan_header(sh, scans, scan_first + blockIdx.x, B);
     const uint32_t nsub = sh.scan_nsub;
     const size_t g0 = sh.sc.sub0;
+    const uint32_t n_streams = sh.sc.n_streams;
+    const bool use_bitmap = n_streams > 1 && (nsub + 31) / 32 <= bitmap_words;
+    const bool lut_in_smem = sh.sc.lut_len <= lut_cap;
+    if (lut_in_smem)
+        for (uint32_t i = tid; i < sh.sc.lut_len; i += kChainThreads) s_lut[i] = __ldg(B.lut + sh.sc.lut_off + i);
+    if (use_bitmap) {
+        for (uint32_t i = tid; i < (nsub + 31) / 32; i += kChainThreads) s_heads[i] = 0u;
+        __syncthreads();
+        for (uint32_t m = tid; m < n_streams; m += kChainThreads) {
+            const uint32_t l = B.stream_sub[sh.sc.stream0 + m];
+            if (l < nsub) atomicOr(&s_heads[l >> 5], 1u << (l & 31));
+        }
+    }
+    __syncthreads();
     {
-        // Lane i owns boundary lb = (i + 1) * T (+ 32 * T * k): it may only rewrite subsequences of its own
-        // range [lb, lb + T), so lanes never race; a correction that reaches the end of the range is picked
-        // up by the owner of the next boundary in the next pass.  Passes repeat until nothing mismatches.
         GlobalSrc src{B.words, (uint32_t)B.words_len};
         const uint32_t* const glut = B.lut + sh.sc.lut_off;
         uint32_t repairs = 0;
         for (;;) {
             bool any = false;
-            for (uint32_t lb0 = T; lb0 < nsub; lb0 += 32 * T) {
-                const uint32_t lb = lb0 + lane * T;
+            for (uint32_t lb0 = T; lb0 < nsub; lb0 += kChainThreads * T) {
+                const uint32_t lb = lb0 + tid * T;
                 if (lb < nsub) {
                     uint32_t cur = lb;
                     uint64_t st = B.sub_exit[g0 + cur - 1];
@@ -444,7 +439,8 @@ __global__ void __launch_bounds__(128) chain_kernel(const bj_scan* __restrict__ 
                             B.sub_entry[g0 + cur] = st;
                             uint64_t ex;
                             SubCount k;
-                            run_sub_core(sh.sc.mode, sh.ctx, glut, src, si.b0, si.own_rel, si.stop_rel, si.end_rel, st, ex, k);
+                            if (lut_in_smem) run_sub_core(sh.sc.mode, sh.ctx, s_lut, src, si.b0, si.own_rel, si.stop_rel, si.end_rel, st, ex, k);
+                            else run_sub_core(sh.sc.mode, sh.ctx, glut, src, si.b0, si.own_rel, si.stop_rel, si.end_rel, st, ex, k);
                             B.sub_exit[g0 + cur] = ex;
                             reinterpret_cast<uint4*>(B.sub_count)[g0 + cur] =
                                 make_uint4(k.blocks, (uint32_t)k.dc[0], (uint32_t)k.dc[1], (uint32_t)k.dc[2]);
@@ -457,54 +453,56 @@ __global__ void __launch_bounds__(128) chain_kernel(const bj_scan* __restrict__ 
                     }
                 }
             }
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, any)) break;
+            __threadfence_block();
+            if (!__syncthreads_or(any ? 1 : 0)) break;
         }
         if (repairs && B.sync_changes) atomicAdd(B.sync_changes, repairs);
     }
-    __syncwarp();
-    __threadfence_block();
-    // segmented exclusive prefix sums: segments start at stream heads
-    uint32_t carry[4] = {0, 0, 0, 0};
-    for (uint32_t base = 0; base < nsub; base += 32) {
-        const uint32_t l = base + lane;
-        uint4 c = make_uint4(0, 0, 0, 0);
-        if (l < nsub) c = reinterpret_cast<const uint4*>(B.sub_count)[g0 + l];
-        // is l a stream head?  (stream_sub is increasing; several heads may fall into one group of 32)
-        bool is_head = false;
-        if (l < nsub) {
-            if (l == 0) is_head = true;
-            else if (sh.sc.n_streams > 1) {
-                uint32_t lo = 0, hi = sh.sc.n_streams - 1;
-                while (lo < hi) {
-                    uint32_t mid = (lo + hi + 1) >> 1;
-                    if (B.stream_sub[sh.sc.stream0 + mid] <= l) lo = mid;
-                    else hi = mid - 1;
-                }
-                is_head = B.stream_sub[sh.sc.stream0 + lo] == l;
-            }
+    __syncthreads();
+    // Segmented exclusive prefix sums (segments = streams): every thread owns a contiguous chunk of the scan's
+    // subsequences; chunk totals go through shared memory; the chunk is walked a second time to write.
+    __shared__ uint32_t s_part[kChainThreads][4];
+    __shared__ uint32_t s_seen[kChainThreads];
+    auto is_head = [&](uint32_t l) -> bool {
+        if (l == 0) return true;
+        if (n_streams <= 1) return false;
+        if (use_bitmap) return (s_heads[l >> 5] >> (l & 31)) & 1u;
+        uint32_t lo = 0, hi = n_streams - 1;  // stream_sub is increasing
+        while (lo < hi) {
+            uint32_t mid = (lo + hi + 1) >> 1;
+            if (B.stream_sub[sh.sc.stream0 + mid] <= l) lo = mid;
+            else hi = mid - 1;
         }
-        uint32_t v[4] = {c.x, c.y, c.z, c.w};
-        uint32_t h = is_head ? 1u : 0u;
-        if (lane == 0 && !is_head)
-            for (int i = 0; i < 4; i++) v[i] += carry[i];
-        const uint32_t own[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {  // inclusive segmented warp scan
-            uint32_t pv[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) pv[i] = __shfl_up_sync(0xffffffffu, v[i], o);
-            uint32_t ph = __shfl_up_sync(0xffffffffu, h, o);
-            if (lane >= o && !h) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) v[i] += pv[i];
-                h = ph;
+        return B.stream_sub[sh.sc.stream0 + lo] == l;
+    };
+    const uint32_t chunk = (nsub + kChainThreads - 1) / kChainThreads;
+    const uint32_t c_lo = min((uint32_t)tid * chunk, nsub), c_hi = min(c_lo + chunk, nsub);
+    const uint4* cnt = reinterpret_cast<const uint4*>(B.sub_count) + g0;
+    {
+        uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, seen = 0;
+        for (uint32_t l = c_lo; l < c_hi; l++) {
+            const uint4 c = cnt[l];
+            if (is_head(l)) {
+                r0 = r1 = r2 = r3 = 0;
+                seen = 1;
             }
+            r0 += c.x; r1 += c.y; r2 += c.z; r3 += c.w;
         }
-        if (l < nsub)
-            reinterpret_cast<uint4*>(B.sub_prefix)[g0 + l] = make_uint4(v[0] - own[0], v[1] - own[1], v[2] - own[2], v[3] - own[3]);
-#pragma unroll
-        for (int i = 0; i < 4; i++) carry[i] = __shfl_sync(0xffffffffu, v[i], 31);
+        s_part[tid][0] = r0; s_part[tid][1] = r1; s_part[tid][2] = r2; s_part[tid][3] = r3;
+        s_seen[tid] = seen;
+    }
+    __syncthreads();
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    for (int p = tid - 1; p >= 0; p--) {  // back to the latest chunk that contains a stream head
+        r0 += s_part[p][0]; r1 += s_part[p][1]; r2 += s_part[p][2]; r3 += s_part[p][3];
+        if (s_seen[p]) break;
+    }
+    uint4* pre = reinterpret_cast<uint4*>(B.sub_prefix) + g0;
+    for (uint32_t l = c_lo; l < c_hi; l++) {
+        const uint4 c = cnt[l];
+        if (is_head(l)) r0 = r1 = r2 = r3 = 0;
+        pre[l] = make_uint4(r0, r1, r2, r3);
+        r0 += c.x; r1 += c.y; r2 += c.z; r3 += c.w;
     }
 }
 
@@ -776,7 +774,13 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         if (phases & BJ_PHASE_SPEC) spec_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
         if (phases & BJ_PHASE_FIX) {
             fix_local_kernel<<<grid, T, 0, st>>>(scans, scan_first, *bufs);
-            chain_kernel<<<(n_scans + 3) / 4, 128, 0, st>>>(scans, scan_first, n_scans, *bufs);
+            // shared-memory bitmap of stream heads: one bit per subsequence of the largest scan, up to 32 KB
+            // (with the 8 KB of LUT and the static arrays this stays below the 48 KB default limit)
+            uint32_t bitmap_words = (max_sub + 31) / 32;
+            if (bitmap_words > 8192u) bitmap_words = 0;
+            const uint32_t chain_lut = lut_cap <= 2048u ? lut_cap : 2048u;  // bitmap + LUT stay below the 48 KB default limit
+            chain_kernel<<<n_scans, kChainThreads, (bitmap_words + chain_lut) * sizeof(uint32_t), st>>>(scans, scan_first, n_scans, *bufs,
+                                                                                                         bitmap_words, chain_lut);
         }
         if (phases & BJ_PHASE_WRITE) write_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
     } else if (mode == BJ_MODE_DC_REFINE) {
