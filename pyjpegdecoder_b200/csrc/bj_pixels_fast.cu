@@ -198,8 +198,11 @@ __device__ __noinline__ void pixel_run_exact(const Tiles<L>& t, int m, int r, in
 // cells 6 - i(a'), so the right half walks its pixels right-to-left over the mirrored chroma columns with the
 // left half's compile-time tap indices; the weight table holds the right half's entries mirrored and with the
 // left/right taps swapped, and luma pairs / RGB pairs are flipped with one byte-permute each.
+// ww: the lane's eight interpolation weight vectors (row r, half hx); loaded once per tile by the caller -- a
+// lane always works on the same (row, half), only the MCU changes from run to run.
 template <class L>
-__device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int hx, bool wide, uint32_t* stats) {
+__device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int hx, const float4 (&ww)[8], bool wide,
+                                          uint32_t* stats) {
     const int ys = (r >> 3) * L::HMAX + hx, yy = r & 7;
     const uint4 yv = *reinterpret_cast<const uint4*>(t.yrow(m, ys, yy));
     const uint32_t flip = (L::HMAX == 2 && hx) ? 0x5476u : 0x3210u;  // byte-permute selector: second operand, halves swapped
@@ -237,10 +240,6 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int h
     } else {
         int j = (L::VMAX == 2) ? ((r == 15) ? 6 : (7 * r) / 15) : r;
         int j2 = j < 7 ? j + 1 : 7;
-        const float4* w = t.w + r * kWStride + 8 * hx;
-        float4 ww[8];
-#pragma unroll
-        for (int p = 0; p < 8; p++) ww[p] = w[p];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             float* o = k ? crm : cbm;
@@ -478,14 +477,21 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
     const int cols = min(M * L::MCU_W, (int)im.width - x0);
     const int rows = min(L::MCU_H, (int)im.height - y0);
     const int nunits = M * L::MCU_H * L::HMAX;  // 8-pixel runs: (MCU, half, row)
+    {
+        // 32 is a multiple of MCU_H * HMAX: lane -> (row, half) is the same in every pass, only the MCU advances
+        static_assert(32 % (L::MCU_H * L::HMAX) == 0, "lane -> (row, half) must not depend on the pass");
+        const int r = lane % L::MCU_H, hx = (lane / L::MCU_H) % L::HMAX;
+        float4 ww[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) ww[p] = L::UPS ? t.w[r * kWStride + 8 * hx + p] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-    for (int u0 = 0; u0 < nunits; u0 += 32) {
-        const int u = u0 + lane;
-        const int r = u % L::MCU_H, mh = u / L::MCU_H;
-        const int hx = mh % L::HMAX, m = mh / L::HMAX;
-        if (u < nunits && r < rows) {
-            const bool wide = ((wide_mask >> (m * L::BPM)) & ((1u << L::BPM) - 1u)) != 0u;
-            pixel_run<L>(t, m, r, hx, wide, stats);
+        for (int u0 = 0; u0 < nunits; u0 += 32) {
+            const int u = u0 + lane;
+            const int m = u / (L::MCU_H * L::HMAX);
+            if (u < nunits && r < rows) {
+                const bool wide = ((wide_mask >> (m * L::BPM)) & ((1u << L::BPM) - 1u)) != 0u;
+                pixel_run<L>(t, m, r, hx, ww, wide, stats);
+            }
         }
     }
     __syncwarp();
