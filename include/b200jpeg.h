@@ -249,6 +249,12 @@ int bj_host_walk(const uint8_t* data, uint64_t n, bj_host_entry* entries, int ma
 void bj_host_walk_batch(const uint8_t* raw, const uint64_t* off, const uint64_t* size, int n_files,
                         bj_host_entry* entries, int max_entries, int32_t* counts, int n_threads);
 
+/* bj_host_walk_batch plus a 128-bit hash per file (key_hash[2*i], key_hash[2*i+1]) of everything that determines
+ * the parse (marker sequence + payloads of SOFn/DHT/DQT/DRI/SOS/DNL/EOI + one tag per entropy-coded run): files
+ * with equal hashes share one parsed template on the host. */
+void bj_host_walk_batch_keys(const uint8_t* raw, const uint64_t* off, const uint64_t* size, int n_files,
+                             bj_host_entry* entries, int max_entries, int32_t* counts, uint64_t* key_hash, int n_threads);
+
 /* Threaded gather of n_files host buffers into one packed buffer: memcpy(dst + off[i], src[i], size[i]). */
 void bj_host_pack(const uint8_t* const* src, const uint64_t* size, const uint64_t* off, int n_files, uint8_t* dst,
                   int n_threads);

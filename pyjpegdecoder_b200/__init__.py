@@ -10,7 +10,7 @@ No CPU fallback: without the CUDA library or a GPU the decoder raises NativeLibr
 from .errors import CorruptedJpeg, JpegError, NativeLibraryError, NotJpeg, UnsupportedJpeg
 from .parser import parse_jpeg
 
-__all__ = ["JpegDecoder", "decode_batch", "decode_files_multi_gpu", "parse_jpeg", "JpegError", "NotJpeg",
+__all__ = ["JpegDecoder", "decode_batch", "decode_stream", "decode_files_multi_gpu", "parse_jpeg", "JpegError", "NotJpeg",
            "CorruptedJpeg", "UnsupportedJpeg", "NativeLibraryError"]
 
 
@@ -19,6 +19,9 @@ def __getattr__(name):
     if name in ("JpegDecoder", "decode_batch"):
         from . import decoder
         return getattr(decoder, name)
+    if name == "decode_stream":
+        from .loader import decode_stream
+        return decode_stream
     if name == "decode_files_multi_gpu":
         from .multigpu import decode_files_multi_gpu
         return decode_files_multi_gpu

@@ -115,6 +115,70 @@ extern "C" void bj_host_walk_batch(const uint8_t* raw, const uint64_t* off, cons
     for (auto& x : th) x.join();
 }
 
+// 128-bit hash of what determines a file's parse: the sequence of markers, the payload of every segment that
+// changes the parse (SOFn, DHT, DQT, DRI, SOS, DNL, EOI) and one tag per entropy-coded run.  Files with equal
+// hashes share one parsed template on the host (fastplan.py); two independent 64-bit multiply-mix streams make an
+// accidental collision a 2^-128 event.
+static inline uint64_t mix64(uint64_t h, uint64_t v, uint64_t k) {
+    h ^= v;
+    h *= k;
+    h ^= h >> 29;
+    return h;
+}
+static void key_hash_one(const uint8_t* d, const bj_host_entry* e, int count, uint64_t out[2]) {
+    uint64_t a = 0x9E3779B97F4A7C15ull, b = 0xC2B2AE3D27D4EB4Full;
+    for (int i = 0; i < count; i++) {
+        const uint32_t m = e[i].marker;
+        if (m == 0x100) {
+            a = mix64(a, 0xE0E0E0E0ull, 0xFF51AFD7ED558CCDull);
+            b = mix64(b, 0x0E0E0E0Eull, 0xC4CEB9FE1A85EC53ull);
+            continue;
+        }
+        const bool key = (m >= 0xC0 && m <= 0xCF) || m == 0xDB || m == 0xDD || m == 0xDA || m == 0xDC || m == 0xD9;
+        if (!key) continue;
+        const uint64_t len = e[i].end - e[i].start;
+        a = mix64(a, ((uint64_t)m << 32) | (len & 0xFFFFFFFFull), 0xFF51AFD7ED558CCDull);
+        b = mix64(b, ((uint64_t)len << 8) | m, 0xC4CEB9FE1A85EC53ull);
+        const uint8_t* p = d + e[i].start;
+        uint64_t k = 0;
+        for (; k + 8 <= len; k += 8) {
+            uint64_t v;
+            memcpy(&v, p + k, 8);
+            a = mix64(a, v, 0xFF51AFD7ED558CCDull);
+            b = mix64(b, v, 0xC4CEB9FE1A85EC53ull);
+        }
+        uint64_t v = 0;
+        for (int s = 0; k < len; k++, s += 8) v |= (uint64_t)p[k] << s;
+        a = mix64(a, v, 0xFF51AFD7ED558CCDull);
+        b = mix64(b, v ^ 0xA5A5A5A5A5A5A5A5ull, 0xC4CEB9FE1A85EC53ull);
+    }
+    out[0] = a;
+    out[1] = b;
+}
+
+// bj_host_walk_batch + the key hash of every file (key_hash: [n_files][2]; files whose walk failed get 0, 0).
+extern "C" void bj_host_walk_batch_keys(const uint8_t* raw, const uint64_t* off, const uint64_t* size, int n_files,
+                                        bj_host_entry* entries, int max_entries, int32_t* counts, uint64_t* key_hash,
+                                        int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_files) n_threads = n_files > 0 ? n_files : 1;
+    auto work = [&](int t) {
+        for (int i = t; i < n_files; i += n_threads) {
+            bj_host_entry* e = entries + (size_t)i * max_entries;
+            counts[i] = walk_one(raw + off[i], size[i], e, max_entries);
+            key_hash[2 * i] = key_hash[2 * i + 1] = 0;
+            if (counts[i] > 0) key_hash_one(raw + off[i], e, counts[i], key_hash + 2 * i);
+        }
+    };
+    if (n_threads == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+}
+
 // Copy n_files separate host buffers into one packed buffer (dst + off[i]) with n_threads host threads:
 // a single Python-level copy loop tops out near 5 GB/s, far below what the H2D copy that follows can take.
 extern "C" void bj_host_pack(const uint8_t* const* src, const uint64_t* size, const uint64_t* off, int n_files, uint8_t* dst,

@@ -47,39 +47,55 @@ class JpegDecoder:
                  _index: int = 0):
         if isinstance(file, (bytes, bytearray, memoryview)):
             self.file_path = None
-            data = bytes(file)
         else:
             self.file_path = file if isinstance(file, Path) else Path(file)
-            data = _read(file) if _batch is None else b""
-        self.file_size = len(data) if _batch is None else _batch.plan.parsed[_index].file_size
         if _batch is None:
+            data = _read(file)
+            self.file_size = len(data)
             p = parsed if parsed is not None else parse_jpeg(data)
             _batch = decode_batch_on_device([data], device=device, parsed=[p])
             _index = 0
         self._batch = _batch
         self._index = _index
-        p = _batch.plan.parsed[_index]
-        self._parsed = p
-        self.scan_finished = p.finished
-        self.scan_mode = "progressive_dct" if p.progressive else "baseline_dct"
-        self.image_width = p.width
-        self.image_height = p.height
-        self.color_components = {
-            c.id: ColorComponent(name=_NAMES[c.order], order=c.order, vertical_sampling=c.v, horizontal_sampling=c.h,
-                                 quantization_table_id=c.tq, repeat=c.h * c.v, shape=(8 * c.h, 8 * c.v))
-            for c in p.components}
-        self.sample_shape = (8 * p.hmax, 8 * p.vmax)
-        self.restart_interval = p.restart_interval
-        self.scan_count = len(p.scans)
-        self.scan_amount = p.scan_amount
-        self.array_width, self.array_height = p.canvas_size
-        self.array_depth = p.ncomp
-        last = p.scans[-1]
-        self.mcu_count_h, self.mcu_count_v = last.mcus_x, last.mcus_y
-        self.mcu_count = last.mcus_x * last.mcus_y
         self._image_array = None
         if verbose:
             print(f"Decoded {self.image_width} x {self.image_height} {self.scan_mode} image, {self.scan_count} scan(s)")
+
+    # The descriptive attributes of the reference (image_width, scan_mode, color_components, ...) are derived from
+    # the parsed headers the first time one of them is read: a batch of thousands of results should not pay for
+    # thousands of attribute sets nobody may look at.
+    _LAZY = frozenset(("_parsed", "scan_finished", "scan_mode", "image_width", "image_height", "color_components",
+                       "sample_shape", "restart_interval", "scan_count", "scan_amount", "array_width", "array_height",
+                       "array_depth", "mcu_count_h", "mcu_count_v", "mcu_count", "file_size"))
+
+    def __getattr__(self, name):
+        if name in JpegDecoder._LAZY and "_batch" in self.__dict__:
+            self._fill()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _fill(self) -> None:
+        p = self._batch.plan.parsed[self._index]
+        d = self.__dict__
+        d["_parsed"] = p
+        d.setdefault("file_size", p.file_size)
+        d["scan_finished"] = p.finished
+        d["scan_mode"] = "progressive_dct" if p.progressive else "baseline_dct"
+        d["image_width"] = p.width
+        d["image_height"] = p.height
+        d["color_components"] = {
+            c.id: ColorComponent(name=_NAMES[c.order], order=c.order, vertical_sampling=c.v, horizontal_sampling=c.h,
+                                 quantization_table_id=c.tq, repeat=c.h * c.v, shape=(8 * c.h, 8 * c.v))
+            for c in p.components}
+        d["sample_shape"] = (8 * p.hmax, 8 * p.vmax)
+        d["restart_interval"] = p.restart_interval
+        d["scan_count"] = len(p.scans)
+        d["scan_amount"] = p.scan_amount
+        d["array_width"], d["array_height"] = p.canvas_size
+        d["array_depth"] = p.ncomp
+        last = p.scans[-1]
+        d["mcu_count_h"], d["mcu_count_v"] = last.mcus_x, last.mcus_y
+        d["mcu_count"] = last.mcus_x * last.mcus_y
 
     # ---- pixels ----------------------------------------------------------------------------------
     @property

@@ -46,22 +46,27 @@ def _lib():
         L.bj_host_walk_batch.restype = None
         L.bj_host_walk_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.bj_host_walk_batch_keys.restype = None
+        L.bj_host_walk_batch_keys.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         _BOUND = True
     return L
 
 
 def walk_batch(raw: np.ndarray, offsets: np.ndarray, sizes: np.ndarray, threads: Optional[int] = None):
-    """Marker walk of every file of the packed buffer.  Returns (entries[n, MAX_ENTRIES], counts[n])."""
+    """Marker walk of every file of the packed buffer.  Returns (entries[n, MAX_ENTRIES], counts[n],
+    key_hash[n, 2]): the 128-bit hash of each file's parse-relevant segments (csrc/bj_host.cu)."""
     n = len(offsets)
     entries = np.empty((n, MAX_ENTRIES), dtype=ENTRY_DTYPE)
     counts = np.empty(n, dtype=np.int32)
+    hashes = np.empty((n, 2), dtype=np.uint64)
     if threads is None:
         threads = min(16, os.cpu_count() or 1)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
-    _lib().bj_host_walk_batch(raw.ctypes.data, offsets.ctypes.data, sizes.ctypes.data, n, entries.ctypes.data,
-                              MAX_ENTRIES, counts.ctypes.data, threads)
-    return entries, counts
+    _lib().bj_host_walk_batch_keys(raw.ctypes.data, offsets.ctypes.data, sizes.ctypes.data, n, entries.ctypes.data,
+                                   MAX_ENTRIES, counts.ctypes.data, hashes.ctypes.data, threads)
+    return entries, counts, hashes
 
 
 class _Template:
@@ -180,66 +185,41 @@ class FastPlan:
         offsets = np.asarray(offsets, dtype=np.int64)
         sizes = np.asarray(sizes, dtype=np.int64)
         self.raw_bytes = int(raw.size)
-        entries, counts = walk_batch(raw, offsets, sizes, threads)
+        entries, counts, hashes = walk_batch(raw, offsets, sizes, threads)
         if (counts == -1).any():
             raise NotJpeg("File is not a JPEG image.")
         if (counts < 0).any():
             raise _Fallback("marker walk overflow")
-        # ---- templates --------------------------------------------------------------------------------
+        # ---- templates: one per distinct key hash (no per-file Python work) -------------------------------
         raw_bytes_view = memoryview(raw)
-        tid = np.empty(n, dtype=np.int64)
-        templates: List[_Template] = []
-        tindex: Dict[int, int] = {}
-        run_start_l, run_end_l, nrun = [], [], np.empty(n, dtype=np.int64)
         cmax = int(counts.max()) if n else 0
-        # plain Python lists: far cheaper to iterate than numpy scalars
-        markers_all = entries["marker"][:, :cmax].tolist()
-        starts_all = entries["start"][:, :cmax].tolist()
-        ends_all = entries["end"][:, :cmax].tolist()
-        counts_l = counts.tolist()
-        offs_l = offsets.tolist()
-        sizes_l = sizes.tolist()
-        key_markers = _KEY_MARKERS
+        valid = np.arange(cmax, dtype=np.int32)[None, :] < counts[:, None]
+        is_run = (entries["marker"][:, :cmax] == ENTROPY_RUN) & valid
+        nrun = is_run.sum(axis=1).astype(np.int64)
+        run_start_l = entries["start"][:, :cmax][is_run]     # row-major: per file, in file order
+        run_end_l = entries["end"][:, :cmax][is_run]
+        hv = np.ascontiguousarray(hashes).view(np.dtype([("a", "<u8"), ("b", "<u8")])).reshape(n)
+        uniq, first_idx, inv = np.unique(hv, return_index=True, return_inverse=True)
+        templates: List[_Template] = []
         cache = FastPlan._cache
-        for i in range(n):
-            c = counts_l[i]
-            mk, st, en = markers_all[i], starts_all[i], ends_all[i]
-            base = offs_l[i]
-            parts = []
-            rs, re_ = [], []
-            for j in range(c):
-                m = mk[j]
-                if m == ENTROPY_RUN:
-                    parts.append(b"\x00E")
-                    rs.append(st[j])
-                    re_.append(en[j])
-                elif m in key_markers:
-                    parts.append(bytes((m,)))
-                    parts.append(raw_bytes_view[base + st[j]:base + en[j]].tobytes())
-            key = b"".join(parts)
-            tpl = cache.get(key)
+        offs_l, sizes_l = offsets.tolist(), sizes.tolist()
+        for u, i0 in zip(uniq.tolist(), first_idx.tolist()):
+            tpl = cache.get(u)
             if tpl is None:
-                data = raw_bytes_view[base:base + sizes_l[i]].tobytes()
+                data = raw_bytes_view[offs_l[i0]:offs_l[i0] + sizes_l[i0]].tobytes()
                 try:
                     tpl = _Template(parse_jpeg(data))
                 except JpegError as e:
                     tpl = e
                 if len(cache) > 4096:
                     cache.clear()
-                cache[key] = tpl
+                cache[u] = tpl
             if isinstance(tpl, Exception):
                 raise tpl
-            if tpl.nscan != len(rs):
-                raise _Fallback("scan count differs from the template")
-            k = tindex.get(id(tpl))
-            if k is None:
-                k = len(templates)
-                tindex[id(tpl)] = k
-                templates.append(tpl)
-            tid[i] = k
-            nrun[i] = len(rs)
-            run_start_l.extend(rs)
-            run_end_l.extend(re_)
+            templates.append(tpl)
+        tid = inv.reshape(n).astype(np.int64)
+        if (np.array([t.nscan for t in templates], dtype=np.int64)[tid] != nrun).any():
+            raise _Fallback("scan count differs from the template")
         run_start = np.asarray(run_start_l, dtype=np.int64)
         run_end = np.asarray(run_end_l, dtype=np.int64)
         run_base = np.concatenate(([0], np.cumsum(nrun)[:-1])) if n else np.zeros(0, np.int64)

@@ -228,6 +228,36 @@ def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot: Optional[in
     return buf, offsets
 
 
+class _LazyViews:
+    """Sequence of per-image (H, W, 3) / (H, W) views of the flat output buffer; a view is created when it is first
+    asked for (a 4096-image batch would otherwise spend tens of milliseconds making views nobody may look at)."""
+
+    def __init__(self, geom, out: torch.Tensor):
+        self._g, self._out = geom, out
+        self._cache: Dict[int, torch.Tensor] = {}
+
+    def __len__(self) -> int:
+        return len(self._g.out_offsets)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        v = self._cache.get(i)
+        if v is None:
+            off, shape = self._g.out_offsets[i], self._g.out_shapes[i]
+            n = 1
+            for d in shape:
+                n *= int(d)
+            v = self._out[off:off + n].view(*shape)
+            self._cache[i] = v
+        return v
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class DecodedBatch:
     """Result of decoding a batch on one device."""
 
@@ -237,7 +267,7 @@ class DecodedBatch:
         self.coef = coef
         self.err = err
         self.stats = stats
-        self.images = image_views(plan.geom, out)   # (H, W, 3) / (H, W) uint8 device tensors
+        self.images = _LazyViews(plan.geom, out)    # (H, W, 3) / (H, W) uint8 device tensors, made on first use
 
     def image_array(self, i: int) -> torch.Tensor:
         """The reference's layout: (W, H, 3) or (W, H) view (jpeg_decoder.py:626, :1373-1386)."""
@@ -400,7 +430,8 @@ class DevicePipeline:
 def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed: Optional[Sequence[ParsedJpeg]] = None,
                            packed: Optional[Tuple[torch.Tensor, List[int]]] = None, check: bool = True,
                            stream: Optional[torch.cuda.Stream] = None, upto_wave: Optional[int] = None,
-                           plan: Optional[BatchPlan] = None, out_kind: int = _native.OUT_RGB) -> DecodedBatch:
+                           plan: Optional[BatchPlan] = None, out_kind: int = _native.OUT_RGB,
+                           raw_dev: Optional[torch.Tensor] = None, raw_ready: Optional[torch.cuda.Event] = None) -> DecodedBatch:
     """Decode a batch of JPEG file images on one GPU.  Returns device tensors; with check=True the
     per-image error words are read back (one synchronisation) and turned into exceptions.
     upto_wave=k stops the entropy stage after the first k scan groups (tests: per-scan parity)."""
@@ -409,12 +440,16 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
         packed = pack_files(datas, reuse_slot=0 if check else None)
     raw_host, offsets = packed
     # start the host->device copy of the file bytes now: it overlaps the host-side planning below
+    # (raw_dev / raw_ready: the caller already started it on another stream -- loader.py)
     dev = require_cuda(device)
     with torch.cuda.device(dev):
         st = stream if stream is not None else torch.cuda.current_stream(dev)
-        with torch.cuda.stream(st):
-            raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=dev)
-            raw_dev.copy_(raw_host, non_blocking=True)
+        if raw_dev is None:
+            with torch.cuda.stream(st):
+                raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=dev)
+                raw_dev.copy_(raw_host, non_blocking=True)
+        elif raw_ready is not None:
+            st.wait_event(raw_ready)
     if plan is None:
         if parsed is None and datas is not None and len(datas) >= FAST_PLAN_MIN_FILES and upto_wave is None:
             from .fastplan import plan_batch

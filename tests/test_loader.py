@@ -1,0 +1,66 @@
+"""Streaming front end (pyjpegdecoder_b200/loader.py): chunking logic on the CPU, equality with decode_batch on the GPU."""
+import io
+
+import numpy as np
+import pytest
+
+
+def _jpeg(w, h, seed, **kw):
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    b = io.BytesIO()
+    Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(b, "JPEG", quality=80, **kw)
+    return b.getvalue()
+
+
+def test_chunks_keeps_order_and_sizes():
+    from pyjpegdecoder_b200.loader import _chunks
+    assert [len(c) for c in _chunks(range(10), 4)] == [4, 4, 2]
+    assert [x for c in _chunks(iter(range(7)), 3) for x in c] == list(range(7))
+    assert list(_chunks([], 5)) == []
+
+
+def test_decode_stream_needs_a_gpu_and_never_falls_back():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pyjpegdecoder_b200 import NativeLibraryError, decode_stream
+    with pytest.raises(NativeLibraryError):
+        next(decode_stream([_jpeg(16, 16, 0)]))
+    with pytest.raises(ValueError):
+        next(decode_stream([_jpeg(16, 16, 0)], chunk=0))
+
+
+def test_host_pack_matches_python_copy():
+    """bj_host_pack (threaded gather in C) against a plain Python copy."""
+    from pyjpegdecoder_b200.pipeline import pack_files
+    rng = np.random.default_rng(3)
+    datas = [rng.integers(0, 256, int(n), dtype=np.uint8).tobytes() for n in rng.integers(1, 5000, 40)]
+    buf, offs = pack_files(datas, pin=False)
+    v = buf.numpy()
+    for d, o in zip(datas, offs):
+        assert o % 16 == 0 and bytes(v[o:o + len(d)]) == d
+
+
+@pytest.mark.gpu
+def test_decode_stream_equals_decode_batch(tmp_path):
+    from pyjpegdecoder_b200 import decode_batch, decode_stream
+    files = []
+    for i in range(37):
+        kw = {}
+        if i % 5 == 1:
+            kw["progressive"] = True
+        if i % 3 == 0:
+            kw["subsampling"] = i % 3
+        data = _jpeg(40 + 13 * (i % 7), 24 + 9 * (i % 5), i, **kw)
+        if i % 2:
+            path = tmp_path / f"f{i}.jpg"
+            path.write_bytes(data)
+            files.append(path)
+        else:
+            files.append(data)
+    ref = decode_batch(files, device="cuda:0")
+    out = [d for chunk in decode_stream(iter(files), chunk=8, device="cuda:0") for d in chunk]
+    assert len(out) == len(ref) == 37
+    for a, b in zip(out, ref):
+        assert np.array_equal(a.image_array, b.image_array)

@@ -47,7 +47,18 @@ def main():
         y, x = np.mgrid[0:2340, 0:4160]
         img = np.clip(np.stack([128 + 90 * np.sin(x / 37 + y / 53), 128 + 90 * np.cos(x / 29 - y / 41),
                                 128 + 90 * np.sin((x + y) / 61)], -1) + rng.normal(0, 12, (2340, 4160, 3)), 0, 255).astype(np.uint8)
-    for kw, nm in ((dict(progressive=True), "C3 prog 4160x2340"), (dict(progressive=True, restart_marker_rows=1), "C3 prog +DRI"),
+    # SURVEY.md section 8d generator for config C3: quality 75
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", quality=75, subsampling=2, progressive=True)
+    run("C3 prog 4160x2340 q75 x1", [b.getvalue()])
+    try:
+        import oracle
+        t0 = time.perf_counter()
+        oracle.decode(b.getvalue(), want=("rgb",))
+        print(f"    CPU oracle (1 core) on the same file: {1e3 * (time.perf_counter() - t0):.0f} ms")
+    except Exception as e:  # noqa
+        print("    oracle unavailable:", e)
+    for kw, nm in ((dict(progressive=True), "C3 prog 4160x2340 q90 (dense worst case)"), (dict(progressive=True, restart_marker_rows=1), "C3 prog +DRI"),
                    (dict(), "C3-size baseline")):
         b = io.BytesIO()
         Image.fromarray(img).save(b, "JPEG", quality=90, subsampling=2, **kw)
