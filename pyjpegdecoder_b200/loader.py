@@ -55,7 +55,7 @@ class _Uploader:
         slot = k % _N_SLOTS
         if self.done[slot] is not None:
             self.done[slot].synchronize()          # the copy that last read this pinned slot has finished
-        packed = pack_files(datas, pin=True, reuse_slot=1000 + slot)
+        packed = pack_files(datas, pin=True, reuse_slot=("loader", id(self), slot))
         raw_host, offsets = packed
         with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
             raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=self.dev)
@@ -69,6 +69,14 @@ class _Uploader:
         else:
             plan = BatchPlan([parse_jpeg(d) for d in datas], offsets, raw_host.numel())
         return list(files), packed, plan, raw_dev, ev
+
+
+    def close(self) -> None:
+        from .pipeline import _PINNED_POOL
+        for slot in range(_N_SLOTS):
+            if self.done[slot] is not None:
+                self.done[slot].synchronize()
+            _PINNED_POOL.pop(("loader", id(self), slot), None)
 
 
 def _check(batch) -> None:
@@ -86,6 +94,13 @@ def decode_stream(files: Iterable[Source], chunk: int = 512, device: Optional[Un
     up = _Uploader(device)
     it = _chunks(files, chunk)
     depth = _N_SLOTS - 1                     # chunks prepared ahead of the one being enqueued
+    try:
+        yield from _stream(up, it, depth, device)
+    finally:
+        up.close()
+
+
+def _stream(up, it, depth, device):
     with ThreadPoolExecutor(_WORKERS) as worker:
         queue = []
         k = 0

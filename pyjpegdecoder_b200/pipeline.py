@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -187,21 +188,53 @@ class BatchPlan:
                              if g.mode in (0, 1, 3)) if any(g.mode in (0, 1, 3) for g in self.groups) else 1
 
 
-_PINNED_POOL: Dict[int, torch.Tensor] = {}
+_PINNED_POOL: Dict[object, torch.Tensor] = {}     # keyed slots (one owner each, e.g. loader._Uploader)
+_PINNED_FREE: List[torch.Tensor] = []             # checkout / release list shared by all threads
+_PINNED_LOCK = threading.Lock()
 
 
-def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot: Optional[int] = None) -> Tuple[torch.Tensor, List[int]]:
+def _pinned_take(total: int) -> torch.Tensor:
+    with _PINNED_LOCK:
+        best = None
+        for i, t in enumerate(_PINNED_FREE):
+            if t.numel() >= total and (best is None or t.numel() < _PINNED_FREE[best].numel()):
+                best = i
+        if best is not None:
+            return _PINNED_FREE.pop(best)
+    return torch.empty(max(total, 1 << 20) * 5 // 4, dtype=torch.uint8, pin_memory=True)
+
+
+def release_pinned(buf: torch.Tensor) -> None:
+    """Give a buffer obtained with pack_files(reuse_slot="checkout") back (after the copy that reads it is done)."""
+    pool = getattr(buf, "_bj_pool", None)
+    if pool is None:
+        return
+    with _PINNED_LOCK:
+        _PINNED_FREE.append(pool)
+        if len(_PINNED_FREE) > 4:                  # keep the largest few
+            _PINNED_FREE.sort(key=lambda t: t.numel())
+            _PINNED_FREE.pop(0)
+
+
+def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot=None) -> Tuple[torch.Tensor, List[int]]:
     """Concatenate file images into one (pinned) host buffer, each file 16-byte aligned.
-    Returns (buffer, offsets); the sizes are len(datas[i]).  reuse_slot: keep the pinned allocation in a
-    small pool and reuse it for the next batch packed into the same slot (pinning memory is slow); the
-    caller must be done with the previous batch of that slot (decode_batch synchronises before returning)."""
+    Returns (buffer, offsets); the sizes are len(datas[i]).  reuse_slot: pinning memory is slow, so allocations
+    are kept.  "checkout": take a buffer from a shared free list and give it back with release_pinned() when the
+    copy out of it has completed (thread safe); any other hashable value: a slot owned by the caller, overwritten
+    by the next pack into the same slot."""
     offsets, total = [], 0
     for d in datas:
         offsets.append(total)
         total += (len(d) + 15) & ~15
     total += 64
     pinned = pin and torch.cuda.is_available()
-    if reuse_slot is not None and pinned:
+    if reuse_slot == "checkout" and pinned:
+        # a buffer from the shared free list (or a new one); the caller gives it back with release_pinned() once the
+        # copy that reads it has completed -- safe with any number of threads / devices decoding at the same time
+        pool = _pinned_take(total)
+        buf = pool[:total]
+        buf._bj_pool = pool
+    elif reuse_slot is not None and pinned:
         pool = _PINNED_POOL.get(reuse_slot)
         if pool is None or pool.numel() < total:
             pool = torch.empty(max(total, 1 << 20) * 5 // 4, dtype=torch.uint8, pin_memory=True)
@@ -437,7 +470,7 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
     upto_wave=k stops the entropy stage after the first k scan groups (tests: per-scan parity)."""
     require_cuda(device)
     if packed is None:
-        packed = pack_files(datas, reuse_slot=0 if check else None)
+        packed = pack_files(datas, reuse_slot="checkout" if check else None)
     raw_host, offsets = packed
     # start the host->device copy of the file bytes now: it overlaps the host-side planning below
     # (raw_dev / raw_ready: the caller already started it on another stream -- loader.py)
@@ -462,5 +495,7 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
     pipe.launch(out_kind=out_kind, upto_group=upto_wave)
     res = pipe.result()
     if check:
-        raise_for_errors(pipe.err.cpu().numpy())
+        err = pipe.err.cpu().numpy()               # synchronises: the upload has long completed
+        release_pinned(raw_host)
+        raise_for_errors(err)
     return res

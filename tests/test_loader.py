@@ -64,3 +64,25 @@ def test_decode_stream_equals_decode_batch(tmp_path):
     assert len(out) == len(ref) == 37
     for a, b in zip(out, ref):
         assert np.array_equal(a.image_array, b.image_array)
+
+
+@pytest.mark.gpu
+def test_concurrent_decode_batch_calls_do_not_share_staging_buffers():
+    """Two host threads decoding different batches at the same time (what the multi-GPU dispatcher does with one
+    thread per GPU): each call must get its own pinned staging buffer."""
+    import threading
+    from pyjpegdecoder_b200 import decode_batch
+    sets = [[_jpeg(64 + 8 * t, 48, 100 * t + i) for i in range(24)] for t in range(2)]
+    ref = [decode_batch(s, device="cuda:0") for s in sets]
+    for _ in range(4):
+        out = [None, None]
+
+        def work(t):
+            out[t] = decode_batch(sets[t], device="cuda:0")
+        th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+        for t in range(2):
+            assert out[t] is not None
+            for a, b in zip(out[t], ref[t]):
+                assert np.array_equal(a.image_array, b.image_array)
