@@ -502,7 +502,12 @@ struct DeepReader {
 template <class Src>
 BJ_HD uint32_t acrefine_parse_chunk(DeepReader<Src>& rd, const ScanCtx& c, const uint32_t* tab, uint32_t end_rel,
                                     const uint8_t* tabs, int nb, uint32_t& eob_run, uint32_t* pos) {
+    // Written for the shortest dependency chain per symbol (this loop runs on ONE lane, every instruction on the
+    // chain costs its full latency): no early exits inside a block -- problems are collected in sticky flags and
+    // looked at once per block; a bad code consumes one bit and ends the block like an EOB, a run past the last
+    // zero-history coefficient (table entry 0xFF >= se) ends the block too.
     const int ss = c.ss, se = c.se;
+    uint32_t bad_code = 0, bad_index = 0;
     for (int i = 0; i < nb; i++) {
         const uint8_t* t = tabs + i * BJ_ACR_TAB_STRIDE;
         if (rd.rel > end_rel + 7) return BJ_ERR_OVERRUN;
@@ -515,25 +520,28 @@ BJ_HD uint32_t acrefine_parse_chunk(DeepReader<Src>& rd, const ScanCtx& c, const
         pos[i] = rd.rel;
         int j = 0;     // zero-history coefficients consumed
         int cd = ss;   // ss + non-zero coefficients refined so far
-        for (;;) {
+        bool more;
+        do {
             const uint32_t pk = rd.peek32();
             const uint32_t e = lut_lookup(tab, pk >> 16);
             const int L = ent_len(e), rs = ent_sym(e);
-            if (L == 0) return BJ_ERR_BAD_CODE;
-            const int r = rs >> 4, s = rs & 15;
-            if (s == 0 && r != 15) {
+            const int r = rs >> 4;
+            bad_code |= (L == 0) ? 1u : 0u;
+            if ((rs & 15) == 0 && r != 15) {  // EOBn (an invalid entry decodes as EOB0 of one bit)
                 eob_run = (1u << r) + (r ? take_bits(pk, L, r) : 0u) - 1u;
-                rd.skip((uint32_t)(L + r + (int)t[BJ_ACR_TAB_NZ] - (cd - ss)));
+                rd.skip((uint32_t)(ent_total(e) + r + (int)t[BJ_ACR_TAB_NZ] - (cd - ss)));
                 break;
             }
             const int tt = j + r;  // ZRL: the 16th zero from here (r = 15)
             const int zp = t[tt];
-            if (zp == 0xFF) return BJ_ERR_COEF_INDEX;
-            rd.skip((uint32_t)(ent_total(e) + (zp - tt) - cd));
+            const int base = ent_total(e) - tt - cd;  // ready before the table value arrives
+            bad_index |= (zp == 0xFF) ? 1u : 0u;
+            more = zp < se;
+            rd.skip((uint32_t)(base + (more || zp != 0xFF ? zp : tt + cd)));
             cd = zp - tt;
             j = tt + 1;
-            if (zp >= se) break;
-        }
+        } while (more);
+        if (bad_code | bad_index) return bad_code ? BJ_ERR_BAD_CODE : BJ_ERR_COEF_INDEX;
     }
     return 0;
 }
