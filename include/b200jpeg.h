@@ -91,7 +91,9 @@ typedef struct bj_image {
  * (self-synchronising Huffman decode), see DESIGN.md.
  * ------------------------------------------------------------------------------------------- */
 #define BJ_SUBSEQ_BITS 1024
+#ifndef BJ_ENTROPY_THREADS
 #define BJ_ENTROPY_THREADS 128 /* subsequences per CTA */
+#endif
 #define BJ_UNSTUFF_TILE 4096   /* raw bytes per CTA of the un-stuffing kernels */
 
 #define BJ_MODE_BASELINE 0  /* baseline_dct_scan           :697-906   */
