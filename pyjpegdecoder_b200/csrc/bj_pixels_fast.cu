@@ -347,19 +347,41 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ bj_image im;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // The descriptor goes to shared memory for later use (visible after the barrier below); what the prologue needs
+    // is read straight from global memory by every thread (one broadcast transaction each), which saves a barrier
+    // and a shared-memory round trip in front of the tile request.
+    const bj_image* const gi = &images[blockIdx.y];
     {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&images[blockIdx.y]);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(gi);
         if (tid < (int)(sizeof(bj_image) / 4)) reinterpret_cast<uint32_t*>(&im)[tid] = src[tid];
     }
-    __syncthreads();
-    if ((int)im.layout != LAYOUT) return;
-    const int strips_per_row = ((int)im.mcus_x + L::STRIP - 1) / L::STRIP;
-    if ((int)blockIdx.x >= (int)im.mcus_y * strips_per_row) return;
+    if ((int)__ldg(&gi->layout) != LAYOUT) return;
+    const int g_mcus_x = (int)__ldg(&gi->mcus_x), g_mcus_y = (int)__ldg(&gi->mcus_y);
+    const int strips_per_row = (g_mcus_x + L::STRIP - 1) / L::STRIP;
+    if ((int)blockIdx.x >= g_mcus_y * strips_per_row) return;
 
-    // ---- CTA-wide tables (the only CTA barrier of the kernel) ---------------------------------------
+    // ---- this warp's tile: requested first, so that the table set-up below runs while it is in flight -------
     float4* wtab = reinterpret_cast<float4*>(smem + kWarps * L::WARP_BYTES);
     int16_t* qt = reinterpret_cast<int16_t*>(smem + kWarps * L::WARP_BYTES + L::W_BYTES);
-    for (int i = tid; i < NCOMP * 64; i += kThreads) qt[i] = qtabs[(size_t)im.qtab[i >> 6] * 64 + (i & 63)];
+    const int my = blockIdx.x / strips_per_row;
+    const int m0 = (blockIdx.x - my * strips_per_row) * L::STRIP + warp * L::MPW;
+    const int M = min(L::MPW, g_mcus_x - m0);
+    Tiles<L> t;
+    t.a = smem + warp * L::WARP_BYTES;
+    t.b = t.a + L::A_BYTES;
+    t.w = wtab;
+    t.qt = qt;
+    const int nblk = M > 0 ? M * L::BPM : 0;
+    if (M > 0) {
+        const uint4* g = reinterpret_cast<const uint4*>(coef + ((int64_t)__ldg(&gi->coef_block0) + ((int64_t)my * g_mcus_x + m0) * L::BPM) * 64);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int i = lane + 32 * k;  // 16-byte chunk index inside the warp's tile
+            if (i < nblk * 8) cp_async16(t.coef_chunk(i >> 3, i & 7), g + i);
+        }
+    }
+    // ---- CTA-wide tables (the only CTA barrier of the kernel) ---------------------------------------
+    for (int i = tid; i < NCOMP * 64; i += kThreads) qt[i] = qtabs[(size_t)__ldg(&gi->qtab[i >> 6]) * 64 + (i & 63)];
     if (L::UPS) {
         for (int i = tid; i < 256; i += kThreads) {
             // entry a' of row b: a' < 8 -> output column a'; a' >= 8 (right half, HMAX == 2) -> column 23 - a',
@@ -374,24 +396,6 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
             bj::up_weights_2d(ii, jj, s, tt, w00, w10, w01, w11);
             wtab[b * kWStride + ap] = mirror ? make_float4((float)w10, (float)w00, (float)w11, (float)w01)
                                              : make_float4((float)w00, (float)w10, (float)w01, (float)w11);
-        }
-    }
-    // ---- this warp's tile ----------------------------------------------------------------------------
-    const int my = blockIdx.x / strips_per_row;
-    const int m0 = (blockIdx.x - my * strips_per_row) * L::STRIP + warp * L::MPW;
-    const int M = min(L::MPW, (int)im.mcus_x - m0);
-    Tiles<L> t;
-    t.a = smem + warp * L::WARP_BYTES;
-    t.b = t.a + L::A_BYTES;
-    t.w = wtab;
-    t.qt = qt;
-    const int nblk = M > 0 ? M * L::BPM : 0;
-    if (M > 0) {
-        const uint4* g = reinterpret_cast<const uint4*>(coef + ((int64_t)im.coef_block0 + ((int64_t)my * im.mcus_x + m0) * L::BPM) * 64);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            int i = lane + 32 * k;  // 16-byte chunk index inside the warp's tile
-            if (i < nblk * 8) cp_async16(t.coef_chunk(i >> 3, i & 7), g + i);
         }
     }
     cp_async_wait_all();
