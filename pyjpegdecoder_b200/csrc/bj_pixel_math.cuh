@@ -97,7 +97,7 @@ BJ_HD float round_tie(float v, float& tie_dist) {
 // ---- chroma interpolation (ResizeGrid, :1588-1626) ---------------------------------------------
 // Output sample a (0..15) of a 16-long axis reads source cell i = floor(7a/15) with fraction
 // s/15, s = 7a mod 15; a = 15 is the right edge of cell 6 (s = 15).
-BJ_HD void up_cell(int a, int& i, int& s) {
+constexpr BJ_HD void up_cell(int a, int& i, int& s) {
     if (a == 15) { i = 6; s = 15; }
     else { i = (7 * a) / 15; s = (7 * a) % 15; }
 }
@@ -109,7 +109,7 @@ BJ_HD void up_cell(int a, int& i, int& s) {
 
 // Integer weights (fifteenths) of the four corners P(i,j), P(i+1,j), P(i,j+1), P(i+1,j+1) for
 // fractions (s,t); exactly one of them is zero (three-tap barycentric interpolation).
-BJ_HD void up_weights_2d(int i, int j, int s, int t, int& w00, int& w10, int& w01, int& w11) {
+constexpr BJ_HD void up_weights_2d(int i, int j, int s, int t, int& w00, int& w10, int& w01, int& w11) {
     bool diag = (BJ_DIAG_MAP >> (7 * i + j)) & 1ull;
     if (diag) {
         if (s >= t) { w00 = 15 - s; w10 = s - t; w01 = 0; w11 = t; }

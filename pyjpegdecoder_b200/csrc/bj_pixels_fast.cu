@@ -146,6 +146,33 @@ __device__ __noinline__ uint32_t ycc_to_rgb_exact_packed(int Yi, float Cbf, floa
     return (uint32_t)__double2int_rn(r) | ((uint32_t)__double2int_rn(g) << 8) | ((uint32_t)__double2int_rn(b) << 16);
 }
 
+// Interpolation weight table of a layout, built at COMPILE time (it only depends on the sampling factors) and
+// placed in global memory: the kernel prologue copies 4 KB instead of recomputing 256 entries per CTA.
+// Entry a' of row b: a' < 8 -> output column a'; a' >= 8 (right half, HMAX == 2) -> column 23 - a', i.e. the right
+// half stored right-to-left with the left/right taps swapped (see pixel_run).
+template <int HMAX, int VMAX>
+struct WeightTable {
+    float4 v[256];
+    constexpr WeightTable() : v{} {
+        for (int i = 0; i < 256; i++) {
+            const int b = i >> 4, ap = i & 15;
+            const bool mirror = (HMAX == 2) && ap >= 8;
+            const int a = mirror ? 23 - ap : ap;
+            int ii = a & 7, s = 0, jj = b & 7, tt = 0;
+            if (HMAX == 2) bj::up_cell(a, ii, s);
+            if (VMAX == 2) bj::up_cell(b, jj, tt);
+            int w00 = 0, w10 = 0, w01 = 0, w11 = 0;
+            bj::up_weights_2d(ii, jj, s, tt, w00, w10, w01, w11);
+            v[i].x = (float)(mirror ? w10 : w00);
+            v[i].y = (float)(mirror ? w00 : w10);
+            v[i].z = (float)(mirror ? w11 : w01);
+            v[i].w = (float)(mirror ? w01 : w11);
+        }
+    }
+};
+template <int HMAX, int VMAX>
+__device__ const WeightTable<HMAX, VMAX> g_weight_table{};
+
 template <int A> struct Cell { static constexpr int i = (A == 15) ? 6 : (7 * A) / 15; };
 
 // Exact colour conversion of a whole 8-pixel run, straight from the sample tile: the out-of-line, compact
@@ -383,20 +410,7 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
     // ---- CTA-wide tables (the only CTA barrier of the kernel) ---------------------------------------
     for (int i = tid; i < NCOMP * 64; i += kThreads) qt[i] = qtabs[(size_t)__ldg(&gi->qtab[i >> 6]) * 64 + (i & 63)];
     if (L::UPS) {
-        for (int i = tid; i < 256; i += kThreads) {
-            // entry a' of row b: a' < 8 -> output column a'; a' >= 8 (right half, HMAX == 2) -> column 23 - a',
-            // i.e. the right half stored right-to-left, with the left/right taps swapped (see pixel_run)
-            const int b = i >> 4, ap = i & 15;
-            const bool mirror = (HMAX == 2) && ap >= 8;
-            const int a = mirror ? 23 - ap : ap;
-            int ii = a & 7, s = 0, jj = b & 7, tt = 0;
-            if (HMAX == 2) bj::up_cell(a, ii, s);
-            if (VMAX == 2) bj::up_cell(b, jj, tt);
-            int w00, w10, w01, w11;
-            bj::up_weights_2d(ii, jj, s, tt, w00, w10, w01, w11);
-            wtab[b * kWStride + ap] = mirror ? make_float4((float)w10, (float)w00, (float)w11, (float)w01)
-                                             : make_float4((float)w00, (float)w10, (float)w01, (float)w11);
-        }
+        for (int i = tid; i < 256; i += kThreads) wtab[(i >> 4) * kWStride + (i & 15)] = g_weight_table<HMAX, VMAX>.v[i];
     }
     cp_async_wait_all();
     __syncthreads();
