@@ -319,7 +319,7 @@ def main():
     dom = max((k for k in stages if "gbs" in stages[k]), key=lambda k: stages[k]["ms"])
     # dram__bytes_read.sum + dram__bytes_write.sum per image from the ncu --set full captures under profiles/
     # (r1g, 64 images per launch): measured DRAM traffic, scaled to the images one launch of this run covers
-    ncu_traffic_per_image = {"pixels": (401.184256e6 + 351.820288e6) / 64, "write": (31.854080e6 + 348.497920e6) / 64,
+    ncu_traffic_per_image = {"pixels": (401.184512e6 + 354.579968e6) / 64, "write": (31.864320e6 + 348.049152e6) / 64,
                              "spec": 24.421376e6 / 64, "fix": (19.857408e6 + 3.593472e6) / 64,
                              "unstuff": (24.596224e6 + 24.657920e6) / 64}
     img_per_launch = n_img / n_chunks
