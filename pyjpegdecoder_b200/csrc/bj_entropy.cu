@@ -521,12 +521,16 @@ struct SmemBlockSink {
     int16_t* coef;
     const bj_scan* sc;
     uint32_t mcu0;
+    uint32_t mcu_next;  // MCU of the next block to commit (0xFFFFFFFF: not known yet)
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void put(int z, int16_t v) {
         *reinterpret_cast<int16_t*>(base + (z >> 3) * (T * 16) + ((z & 7) << 1)) = v;
     }
     __device__ __forceinline__ void commit(uint32_t blk, int slot) {
-        uint32_t mcu = mcu0 + blk / sc->nslots;
+        // blocks are committed in order: the MCU index is tracked instead of divided out for every block
+        if (mcu_next == 0xFFFFFFFFu) mcu_next = mcu0 + blk / sc->nslots;
+        const uint32_t mcu = mcu_next;
+        if (slot + 1 == (int)sc->nslots) mcu_next++;
         uint4* dst = reinterpret_cast<uint4*>(coef + block_address(*sc, mcu, slot) * 64);
         const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -583,7 +587,7 @@ __global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ sc
     const bool ls = sh.lut_in_smem != 0;
     const uint32_t* glut = B.lut + sh.sc.lut_off;
     if (mode == BJ_MODE_BASELINE) {
-        SmemBlockSink sink{reinterpret_cast<unsigned char*>(s_blocks) + tid * 16, B.coef, &sh.sc, si.mcu0};
+        SmemBlockSink sink{reinterpret_cast<unsigned char*>(s_blocks) + tid * 16, B.coef, &sh.sc, si.mcu0, 0xFFFFFFFFu};
         if (ls) err = base_write_run(rd, z, slot, sh.ctx, sh.lut, si.stop_rel, si.end_rel, blk, si.nblk_stream, pred, sink);
         else err = base_write_run(rd, z, slot, sh.ctx, glut, si.stop_rel, si.end_rel, blk, si.nblk_stream, pred, sink);
     } else if (mode == BJ_MODE_DC_FIRST) {
