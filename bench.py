@@ -185,7 +185,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pyjpegdecoder_b200 import _native
     from pyjpegdecoder_b200.parser import parse_jpeg
     from pyjpegdecoder_b200.pipeline import BatchPlan, DevicePipeline, pack_files, raise_for_errors
 

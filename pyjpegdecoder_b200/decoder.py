@@ -17,7 +17,7 @@ import torch
 from .huffman import canonical_codes
 from .layout import ZIGZAG_UV
 from .parser import ParsedJpeg, parse_jpeg
-from .pipeline import DecodedBatch, decode_batch_on_device, pack_files
+from .pipeline import DecodedBatch, decode_batch_on_device
 
 # containers of the reference (:24-25)
 ColorComponent = namedtuple("ColorComponent", "name order vertical_sampling horizontal_sampling quantization_table_id repeat shape")

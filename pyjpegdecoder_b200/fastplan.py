@@ -18,7 +18,7 @@ from __future__ import annotations
 import copy
 import ctypes
 import os
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 

@@ -25,7 +25,7 @@ from .huffman import build_scan_blob
 from .layout import slot0_of
 from .parser import ParsedJpeg, Scan, parse_jpeg
 from .plan import BatchGeometry, scan_levels
-from .stages import DeviceGeometry, image_views, require_cuda, run_pixels, to_device
+from .stages import DeviceGeometry, require_cuda, run_pixels, to_device
 
 SUBSEQ_BITS = 1024
 ENTROPY_THREADS = 128
