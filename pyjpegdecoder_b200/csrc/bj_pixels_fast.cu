@@ -75,10 +75,13 @@ struct Tiles {
     __device__ __forceinline__ unsigned char* yrow(int m, int ys, int y) const {
         return b + m * L::MCU_B + ys * 128 + ((y ^ ((m + ys) & 7)) << 4);
     }
-    // chroma block k (0 = Cb, 1 = Cr) of MCU m, 16-byte chunk c (row y = chunks 2y, 2y+1): 4 floats
-    __device__ __forceinline__ float* cchunk(int m, int k, int c) const {
-        return reinterpret_cast<float*>(b + m * L::MCU_B + L::NY * 128 + k * 256 + (((c ^ (m + L::NY + k)) & 15) << 4));
+    // chroma block k (0 = Cb, 1 = Cr) of MCU m, row y: 8 floats, contiguous; rows are XOR-swizzled in steps of 32
+    // bytes so that the lanes of phase A (one block each, same row at the same time) spread over the banks
+    __device__ __forceinline__ float* crow(int m, int k, int y) const {
+        return reinterpret_cast<float*>(b + m * L::MCU_B + L::NY * 128 + k * 256 + ((y * 32) ^ (((m + k) & 7) * 32)));
     }
+    // 16-byte chunk c of that block (row y = chunks 2y, 2y+1): 4 floats
+    __device__ __forceinline__ float* cchunk(int m, int k, int c) const { return crow(m, k, c >> 1) + (c & 1) * 4; }
 };
 
 // ---- exact recompute of one block by a whole warp (InverseDCT.__call__, :1561-1573) ---------------
@@ -274,10 +277,12 @@ __device__ __forceinline__ void pixel_run(const Tiles<L>& t, int m, int r, int h
                 // window of five source columns: 0..4 for the left half, 7..3 (mirrored) for the right half
                 float p0[5], p1[5];
                 {
-                    const float4 a = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j + hx));
-                    const float4 b = *reinterpret_cast<const float4*>(t.cchunk(m, k, 2 * j2 + hx));
-                    p0[4] = t.cchunk(m, k, 2 * j + 1 - hx)[hx ? 3 : 0];
-                    p1[4] = t.cchunk(m, k, 2 * j2 + 1 - hx)[hx ? 3 : 0];
+                    const float* r0 = t.crow(m, k, j);
+                    const float* r1 = t.crow(m, k, j2);
+                    const float4 a = *reinterpret_cast<const float4*>(r0 + 4 * hx);
+                    const float4 b = *reinterpret_cast<const float4*>(r1 + 4 * hx);
+                    p0[4] = r0[hx ? 3 : 4];   // the fifth column of the window: 4 (left half) or 3 (mirrored right half)
+                    p1[4] = r1[hx ? 3 : 4];
                     p0[0] = hx ? a.w : a.x; p0[1] = hx ? a.z : a.y; p0[2] = hx ? a.y : a.z; p0[3] = hx ? a.x : a.w;
                     p1[0] = hx ? b.w : b.x; p1[1] = hx ? b.z : b.y; p1[2] = hx ? b.y : b.z; p1[3] = hx ? b.x : b.w;
                 }
@@ -465,10 +470,9 @@ bj_pixels_fast_kernel(const bj_image* __restrict__ images, const int16_t* __rest
                                    __byte_perm(__float_as_uint(w[6]), __float_as_uint(w[7]), 0x5410));
                 } else {
                     // rint(v) + 128 = w - MAGIC, exact
-                    *reinterpret_cast<float4*>(t.cchunk(m, comp - 1, 2 * y)) =
-                        make_float4(w[0] - BJ_MAGIC, w[1] - BJ_MAGIC, w[2] - BJ_MAGIC, w[3] - BJ_MAGIC);
-                    *reinterpret_cast<float4*>(t.cchunk(m, comp - 1, 2 * y + 1)) =
-                        make_float4(w[4] - BJ_MAGIC, w[5] - BJ_MAGIC, w[6] - BJ_MAGIC, w[7] - BJ_MAGIC);
+                    float4* row = reinterpret_cast<float4*>(t.crow(m, comp - 1, y));
+                    row[0] = make_float4(w[0] - BJ_MAGIC, w[1] - BJ_MAGIC, w[2] - BJ_MAGIC, w[3] - BJ_MAGIC);
+                    row[1] = make_float4(w[4] - BJ_MAGIC, w[5] - BJ_MAGIC, w[6] - BJ_MAGIC, w[7] - BJ_MAGIC);
                 }
             }
             flagged = maxd > 0.5f - T;
