@@ -39,6 +39,10 @@ constexpr int kWinWords = (T + 1) * (S / 32) + 64;  // bit window of one CTA, in
 constexpr int kMaxLutSmem = 12288;                  // most LUT entries ever staged in shared memory (48 KB)
 
 
+#ifndef BJ_SPEC_WINDOW
+#define BJ_SPEC_WINDOW 0  // 1: spec_kernel stages its bit window in shared memory; 0: reads it through L1 (more CTAs per SM)
+#endif
+
 struct WinSrc {
     const uint32_t* sw;  // shared window, swizzled
     uint32_t w0;         // first word held in the window
@@ -67,6 +71,16 @@ struct CtaShared {
     uint32_t lut_in_smem;
     uint32_t win[kWinWords];
     uint32_t lut[1];   // lut_cap entries follow
+};
+
+// Same without the bit window (kernels that read the bitstream through L1 and spend the shared memory on occupancy)
+struct CtaSharedNoWin {
+    bj_scan sc;
+    ScanCtx ctx;
+    uint32_t scan_nsub;
+    uint32_t lut_cap;
+    uint32_t lut_in_smem;
+    uint32_t lut[1];  // lut_cap entries follow
 };
 
 // The fix-up kernel is latency bound (a few subsequences are re-decoded per round), so it trades the
@@ -102,7 +116,8 @@ __device__ __forceinline__ void load_scan_header(SH& sh, const bj_scan* scans, i
     __syncthreads();
 }
 
-__device__ __forceinline__ void load_scan(CtaShared& sh, const bj_scan* scans, int idx, const bj_entropy_buffers& B,
+template <class SH>
+__device__ __forceinline__ void load_scan(SH& sh, const bj_scan* scans, int idx, const bj_entropy_buffers& B,
                                           uint32_t lut_cap) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[idx]);
     for (int i = threadIdx.x; i < (int)(sizeof(bj_scan) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&sh.sc)[i] = src[i];
@@ -211,8 +226,8 @@ __device__ __forceinline__ void run_sub_core(int mode, const ScanCtx& ctx, const
     ex = pack_state(rd.abs_pos(), z, slot);
 }
 
-template <class Src>
-__device__ __forceinline__ void run_sub(const CtaShared& sh, const bj_entropy_buffers& B, const Src& src, uint64_t b0,
+template <class SH, class Src>
+__device__ __forceinline__ void run_sub(const SH& sh, const bj_entropy_buffers& B, const Src& src, uint64_t b0,
                                         uint32_t own_rel, uint32_t stop_rel, uint32_t end_rel, uint64_t st, uint64_t& ex,
                                         SubCount& k) {
     if (sh.lut_in_smem) run_sub_core(sh.sc.mode, sh.ctx, sh.lut, src, b0, own_rel, stop_rel, end_rel, st, ex, k);
@@ -270,12 +285,17 @@ __global__ void __launch_bounds__(256) plan_kernel(const bj_scan* __restrict__ s
 __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
                                                  uint32_t lut_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#if BJ_SPEC_WINDOW
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
+#else
+    CtaSharedNoWin& sh = *reinterpret_cast<CtaSharedNoWin*>(smem_raw);
+#endif
     load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
     const uint32_t base = blockIdx.y * T;
     if (base >= sh.scan_nsub) return;
     const uint32_t lscan = base + threadIdx.x;
     SubInfo si = locate(sh, B, lscan);
+#if BJ_SPEC_WINDOW
     // window starts where the first thread starts reading
     __shared__ uint64_t first_bit;
     if (threadIdx.x == 0) first_bit = si.l ? si.own - S : si.own;
@@ -283,6 +303,10 @@ __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ sca
     load_window(sh, B, first_bit);
     if (!si.valid) return;
     WinSrc src = win_src(sh, B);
+#else
+    if (!si.valid) return;
+    GlobalSrc src{B.words, (uint32_t)B.words_len};
+#endif
     const int z0 = (sh.sc.mode == BJ_MODE_AC_FIRST) ? sh.sc.ss : 0;
     uint64_t st;
     if (si.l == 0) st = pack_state(si.b0, z0, 0);
@@ -775,7 +799,10 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
         dim3 grid((unsigned)n_scans, (max_sub + T - 1) / T);
         if (grid.y > 65535) return BJ_E_ARG;
-        if (phases & BJ_PHASE_SPEC) spec_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        if (phases & BJ_PHASE_SPEC) {
+            const size_t spec_smem = BJ_SPEC_WINDOW ? smem : sizeof(CtaSharedNoWin) + sizeof(uint32_t) * lut_cap;
+            spec_kernel<<<grid, T, spec_smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        }
         if (phases & BJ_PHASE_FIX) {
             fix_local_kernel<<<grid, T, 0, st>>>(scans, scan_first, *bufs);
             // shared-memory bitmap of stream heads: one bit per subsequence of the largest scan, up to 32 KB
