@@ -39,6 +39,9 @@ constexpr int kWinWords = (T + 1) * (S / 32) + 64;  // bit window of one CTA, in
 constexpr int kMaxLutSmem = 12288;                  // most LUT entries ever staged in shared memory (48 KB)
 
 
+#ifndef BJ_WRITE_WINDOW
+#define BJ_WRITE_WINDOW 0  // same switch for write_kernel
+#endif
 #ifndef BJ_SPEC_WINDOW
 #define BJ_SPEC_WINDOW 0  // 1: spec_kernel stages its bit window in shared memory; 0: reads it through L1 (more CTAs per SM)
 #endif
@@ -583,25 +586,38 @@ struct GlobalCoefSink {  // progressive first scans: single coefficient stores
 __global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
                                                   uint32_t lut_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#if BJ_WRITE_WINDOW
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
-    __shared__ __align__(16) uint32_t s_blocks[T * 32];
     __shared__ uint64_t first_bit;
+#else
+    CtaSharedNoWin& sh = *reinterpret_cast<CtaSharedNoWin*>(smem_raw);
+#endif
+    __shared__ __align__(16) uint32_t s_blocks[T * 32];
     load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
     const uint32_t base = blockIdx.y * T;
     if (base >= sh.scan_nsub) return;
     const int tid = threadIdx.x;
     const uint32_t lscan = base + tid;
     SubInfo si = locate(sh, B, lscan);
+#if BJ_WRITE_WINDOW
     if (tid == 0) first_bit = si.own;
+#endif
     for (int i = tid; i < T * 32; i += T) s_blocks[i] = 0u;
     __syncthreads();
+#if BJ_WRITE_WINDOW
     load_window(sh, B, first_bit);
     if (!si.valid) return;
     WinSrc src = win_src(sh, B);
+    typedef WinSrc SrcT;
+#else
+    if (!si.valid) return;
+    GlobalSrc src{B.words, (uint32_t)B.words_len};
+    typedef GlobalSrc SrcT;
+#endif
     const size_t g = (size_t)sh.sc.sub0 + lscan;
     const uint64_t st = B.sub_entry[g];
     const uint4 pre = reinterpret_cast<const uint4*>(B.sub_prefix)[g];
-    BitReader<WinSrc> rd;
+    BitReader<SrcT> rd;
     rd.seek(&src, si.b0, (uint32_t)(state_pos(st) - si.b0));
     int z = state_z(st), slot = state_slot(st);
     uint32_t blk = pre.x;
@@ -813,7 +829,10 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
             chain_kernel<<<n_scans, kChainThreads, (bitmap_words + chain_lut) * sizeof(uint32_t), st>>>(scans, scan_first, n_scans, *bufs,
                                                                                                          bitmap_words, chain_lut);
         }
-        if (phases & BJ_PHASE_WRITE) write_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        if (phases & BJ_PHASE_WRITE) {
+            const size_t write_smem = BJ_WRITE_WINDOW ? smem : sizeof(CtaSharedNoWin) + sizeof(uint32_t) * lut_cap;
+            write_kernel<<<grid, T, write_smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        }
     } else if (mode == BJ_MODE_DC_REFINE) {
         unsigned gx = (max_blocks + 255) / 256;
         if (gx == 0) gx = 1;
