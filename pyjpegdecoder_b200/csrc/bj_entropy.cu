@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ sca
 // decoded by the first threads of the CTA, so warps stay full even when few subsequences need work.
 // The kernel is latency bound, so it reads the bitstream and the LUTs through L1 instead of staging
 // them (7.7 KB of shared memory per CTA -> 16 CTAs per SM).
-__global__ void __launch_bounds__(T) fix_local_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B) {
+__global__ void __launch_bounds__(T, 16) fix_local_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B) {
     __shared__ CtaSharedLite sh;
     __shared__ uint64_t s_entry[T], s_exit[T];
     __shared__ uint64_t s_b0[T];
