@@ -66,3 +66,27 @@ def test_entropy_logic_random_images_against_oracle(seed):
         p, per_scan, _ = decode_file(data, sub_bits=sub_bits)
         for c, g in enumerate(per_scan[-1]):
             assert np.array_equal(g, np.asarray(ref.coef[c]).reshape(g.shape)), (kw, w, h, c, sub_bits)
+
+
+def test_entropy_logic_survives_corrupted_scans():
+    """Bit flips inside entropy-coded data: the device decode logic (host build) must either decode something or
+    flag an error -- never hang or write outside its blocks (on the GPU that would poison the whole context)."""
+    from pyjpegdecoder_b200.errors import JpegError
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    rng = np.random.default_rng(0)
+    names = golden_case_names()
+    outcomes = {"decoded": 0, "flagged": 0}
+    for _ in range(150):
+        name = names[int(rng.integers(len(names)))]
+        data = bytearray((GOLDEN / "cases" / f"{name}.jpg").read_bytes())
+        p = parse_jpeg(bytes(data))
+        sc = p.scans[int(rng.integers(len(p.scans)))]
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(sc.data_start, max(sc.data_start + 1, sc.data_end)))
+            data[pos] ^= 1 << int(rng.integers(8))
+        try:
+            decode_file(bytes(data))
+            outcomes["decoded"] += 1
+        except (AssertionError, JpegError):
+            outcomes["flagged"] += 1
+    assert outcomes["decoded"] + outcomes["flagged"] == 150 and outcomes["flagged"] > 0
