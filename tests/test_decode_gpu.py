@@ -77,3 +77,33 @@ def test_after_scan_renders(k, golden_meta):
     d = JpegDecoder(cut, device="cuda:0")
     hw3 = np.ascontiguousarray(np.swapaxes(d.image_array, 0, 1))
     assert hashlib.sha256(hw3.tobytes()).hexdigest() == g[f"after_scan_{k}"]["rgb_hw3_sha256"]
+
+
+def test_corrupted_scans_never_poison_the_device():
+    """Bit flips inside the entropy-coded data of many files: every batch either decodes or raises CorruptedJpeg,
+    and a clean file still decodes bit-exactly afterwards (no illegal access, no hang)."""
+    from pyjpegdecoder_b200 import JpegError, decode_batch
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    rng = np.random.default_rng(5)
+    names = golden_case_names()
+    flagged = 0
+    for rnd in range(6):
+        batch = []
+        for _ in range(24):
+            name = names[int(rng.integers(len(names)))]
+            data = bytearray((GOLDEN / "cases" / f"{name}.jpg").read_bytes())
+            p = parse_jpeg(bytes(data))
+            sc = p.scans[int(rng.integers(len(p.scans)))]
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(sc.data_start, max(sc.data_start + 1, sc.data_end)))
+                data[pos] ^= 1 << int(rng.integers(8))
+            batch.append(bytes(data))
+        try:
+            decode_batch(batch, device="cuda:0")
+        except JpegError:
+            flagged += 1
+    assert flagged > 0
+    name = names[0]
+    data, z = _case(name)
+    d = decode_batch([data] * 4, device="cuda:0")[0]
+    assert np.array_equal(d.image_array, z["rgb"])
