@@ -86,3 +86,38 @@ def test_concurrent_decode_batch_calls_do_not_share_staging_buffers():
             assert out[t] is not None
             for a, b in zip(out[t], ref[t]):
                 assert np.array_equal(a.image_array, b.image_array)
+
+
+def test_lazy_views_and_lazy_decoder_attributes_on_cpu():
+    """_LazyViews / JpegDecoder's lazy attributes need no GPU: exercise them on a CPU tensor with a real parse."""
+    import torch
+    from pyjpegdecoder_b200.decoder import JpegDecoder
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    from pyjpegdecoder_b200.pipeline import _LazyViews
+    from pyjpegdecoder_b200.plan import BatchGeometry
+
+    datas = [_jpeg(40, 24, 1), _jpeg(17, 33, 2, progressive=True)]
+    parsed = [parse_jpeg(d) for d in datas]
+    geom = BatchGeometry(parsed)
+    out = torch.arange(geom.out_bytes, dtype=torch.int64).to(torch.uint8)
+    views = _LazyViews(geom, out)
+    assert len(views) == 2 and views[0].shape == (24, 40, 3) and views[-1].shape == (33, 17, 3)
+    assert views[1].data_ptr() == out.data_ptr() + geom.out_offsets[1] and views[1] is views[1]
+    assert [tuple(v.shape) for v in views] == [(24, 40, 3), (33, 17, 3)]
+
+    class FakePlan:
+        pass
+
+    class FakeBatch:
+        pass
+    fb = FakeBatch()
+    fb.plan = FakePlan()
+    fb.plan.parsed = parsed
+    fb.images = views
+    d = JpegDecoder(datas[1], _batch=fb, _index=1)
+    assert "image_width" not in d.__dict__              # nothing materialised yet
+    assert (d.image_width, d.image_height, d.scan_mode) == (17, 33, "progressive_dct")
+    assert d.scan_count == len(parsed[1].scans) and d.file_size == len(datas[1])
+    assert d.image_array.shape == (17, 33, 3)           # the reference's x-major layout
+    with pytest.raises(AttributeError):
+        d.no_such_attribute
