@@ -261,6 +261,10 @@ void bj_host_walk_batch_keys(const uint8_t* raw, const uint64_t* off, const uint
 void bj_host_pack(const uint8_t* const* src, const uint64_t* size, const uint64_t* off, int n_files, uint8_t* dst,
                   int n_threads);
 
+/* bj_host_pack + bj_host_walk_batch_keys in one pass (each file is walked right after it was copied, cache-hot). */
+void bj_host_pack_walk_keys(const uint8_t* const* src, const uint64_t* size, const uint64_t* off, int n_files, uint8_t* dst,
+                            bj_host_entry* entries, int max_entries, int32_t* counts, uint64_t* key_hash, int n_threads);
+
 /*
  * Pixel stages.  Replaces, for a whole batch of images in one launch:
  *   undo_zigzag * Q              jpeg_decoder.py:1648-1662, :869, :1347-1348   (int16 product wraps)

@@ -180,12 +180,15 @@ class FastPlan:
 
     _cache: Dict[bytes, object] = {}
 
-    def __init__(self, raw: np.ndarray, offsets: Sequence[int], sizes: Sequence[int], threads: Optional[int] = None):
+    def __init__(self, raw: np.ndarray, offsets: Sequence[int], sizes: Sequence[int], threads: Optional[int] = None,
+                 walked=None):
+        """walked: (entries, counts, key_hash) if the marker walk was already done while the files were packed
+        (pipeline.pack_files(walk=True))."""
         n = len(offsets)
         offsets = np.asarray(offsets, dtype=np.int64)
         sizes = np.asarray(sizes, dtype=np.int64)
         self.raw_bytes = int(raw.size)
-        entries, counts, hashes = walk_batch(raw, offsets, sizes, threads)
+        entries, counts, hashes = walked if walked is not None else walk_batch(raw, offsets, sizes, threads)
         if (counts == -1).any():
             raise NotJpeg("File is not a JPEG image.")
         if (counts < 0).any():
@@ -341,11 +344,11 @@ class _Fallback(Exception):
     """Internal: the fast planner cannot handle this batch; use the per-file Python path."""
 
 
-def plan_batch(raw_host, offsets: Sequence[int], sizes: Sequence[int], threads: Optional[int] = None):
+def plan_batch(raw_host, offsets: Sequence[int], sizes: Sequence[int], threads: Optional[int] = None, walked=None):
     """Plan for a packed batch: FastPlan when possible, else the per-file BatchPlan (same attributes)."""
     raw_np = raw_host.numpy() if hasattr(raw_host, "numpy") else np.asarray(raw_host)
     try:
-        return FastPlan(raw_np, offsets, sizes, threads)
+        return FastPlan(raw_np, offsets, sizes, threads, walked)
     except _Fallback:
         from .pipeline import BatchPlan
         mv = memoryview(raw_np)

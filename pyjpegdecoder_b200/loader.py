@@ -55,7 +55,7 @@ class _Uploader:
         slot = k % _N_SLOTS
         if self.done[slot] is not None:
             self.done[slot].synchronize()          # the copy that last read this pinned slot has finished
-        packed = pack_files(datas, pin=True, reuse_slot=("loader", id(self), slot))
+        packed = pack_files(datas, pin=True, reuse_slot=("loader", id(self), slot), walk=len(datas) >= FAST_PLAN_MIN_FILES)
         raw_host, offsets = packed
         with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
             raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=self.dev)
@@ -65,7 +65,7 @@ class _Uploader:
         self.done[slot] = ev
         if len(datas) >= FAST_PLAN_MIN_FILES:
             from .fastplan import plan_batch
-            plan = plan_batch(raw_host, offsets, [len(d) for d in datas])
+            plan = plan_batch(raw_host, offsets, [len(d) for d in datas], walked=getattr(raw_host, "_bj_walk", None))
         else:
             plan = BatchPlan([parse_jpeg(d) for d in datas], offsets, raw_host.numel())
         return list(files), packed, plan, raw_dev, ev

@@ -216,7 +216,7 @@ def release_pinned(buf: torch.Tensor) -> None:
             _PINNED_FREE.pop(0)
 
 
-def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot=None) -> Tuple[torch.Tensor, List[int]]:
+def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot=None, walk: bool = False) -> Tuple[torch.Tensor, List[int]]:
     """Concatenate file images into one (pinned) host buffer, each file 16-byte aligned.
     Returns (buffer, offsets); the sizes are len(datas[i]).  reuse_slot: pinning memory is slow, so allocations
     are kept.  "checkout": take a buffer from a shared free list and give it back with release_pinned() when the
@@ -244,16 +244,31 @@ def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot=None) -> Tup
         buf = torch.empty(total, dtype=torch.uint8, pin_memory=pinned)
     n = len(datas)
     if n >= 8 and all(type(d) is bytes for d in datas):
-        # threaded gather in C (csrc/bj_host.cu): the pointers come straight from the bytes objects
+        # threaded gather in C (csrc/bj_host.cu): the pointers come straight from the bytes objects.  With
+        # walk=True every file is also marker-walked and hashed right after it was copied (cache-hot); the result
+        # rides along on the returned tensor (buf._bj_walk) and saves fastplan.plan_batch its own pass over the bytes.
         L = _native.lib()
         if not getattr(L, "_pack_bound", False):
             L.bj_host_pack.restype = None
             L.bj_host_pack.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+            L.bj_host_pack_walk_keys.restype = None
+            L.bj_host_pack_walk_keys.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
             L._pack_bound = True
         ptrs = (ctypes.c_char_p * n)(*datas)
         sizes = np.fromiter((len(d) for d in datas), dtype=np.uint64, count=n)
         offs = np.asarray(offsets, dtype=np.uint64)
-        L.bj_host_pack(ptrs, sizes.ctypes.data, offs.ctypes.data, n, buf.data_ptr(), min(16, os.cpu_count() or 1))
+        threads = min(16, os.cpu_count() or 1)
+        if walk:
+            from .fastplan import ENTRY_DTYPE, MAX_ENTRIES
+            entries = np.empty((n, MAX_ENTRIES), dtype=ENTRY_DTYPE)
+            counts = np.empty(n, dtype=np.int32)
+            hashes = np.empty((n, 2), dtype=np.uint64)
+            L.bj_host_pack_walk_keys(ptrs, sizes.ctypes.data, offs.ctypes.data, n, buf.data_ptr(), entries.ctypes.data,
+                                     MAX_ENTRIES, counts.ctypes.data, hashes.ctypes.data, threads)
+            buf._bj_walk = (entries, counts, hashes)
+        else:
+            L.bj_host_pack(ptrs, sizes.ctypes.data, offs.ctypes.data, n, buf.data_ptr(), threads)
     else:
         view = buf.numpy()
         for d, off in zip(datas, offsets):
@@ -470,7 +485,8 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
     upto_wave=k stops the entropy stage after the first k scan groups (tests: per-scan parity)."""
     require_cuda(device)
     if packed is None:
-        packed = pack_files(datas, reuse_slot="checkout" if check else None)
+        packed = pack_files(datas, reuse_slot="checkout" if check else None,
+                            walk=parsed is None and plan is None and len(datas) >= FAST_PLAN_MIN_FILES and upto_wave is None)
     raw_host, offsets = packed
     # start the host->device copy of the file bytes now: it overlaps the host-side planning below
     # (raw_dev / raw_ready: the caller already started it on another stream -- loader.py)
@@ -486,7 +502,7 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
     if plan is None:
         if parsed is None and datas is not None and len(datas) >= FAST_PLAN_MIN_FILES and upto_wave is None:
             from .fastplan import plan_batch
-            plan = plan_batch(raw_host, offsets, [len(d) for d in datas])
+            plan = plan_batch(raw_host, offsets, [len(d) for d in datas], walked=getattr(raw_host, "_bj_walk", None))
         else:
             if parsed is None:
                 parsed = [parse_jpeg(d) for d in datas]

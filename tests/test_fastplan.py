@@ -85,3 +85,30 @@ def test_scan_levels_of_the_default_progressive_script():
                      "ac_refine", "ac_refine", "ac_refine"]
     assert scan_levels(p) == [0, 0, 0, 0, 0, 1, 1, 1, 1, 2]
     assert scan_levels(p, serial=True) == list(range(10))
+
+
+def test_pack_with_walk_gives_the_same_walk_and_plan():
+    """pack_files(walk=True) (copy + marker walk + key hash in one pass) against the separate walk, and the plans
+    built from either."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from pyjpegdecoder_b200.fastplan import plan_batch, walk_batch
+    from pyjpegdecoder_b200.pipeline import pack_files
+    rng = np.random.default_rng(11)
+    datas = []
+    for i in range(12):
+        b = io.BytesIO()
+        Image.fromarray(rng.integers(0, 256, (24 + 8 * (i % 3), 40, 3), dtype=np.uint8)).save(
+            b, "JPEG", quality=70, progressive=bool(i % 2), subsampling=i % 3)
+        datas.append(b.getvalue())
+    buf, offs = pack_files(datas, pin=False, walk=True)
+    entries, counts, hashes = buf._bj_walk
+    e2, c2, h2 = walk_batch(buf.numpy(), np.asarray(offs), np.asarray([len(d) for d in datas]))
+    assert np.array_equal(counts, c2) and np.array_equal(hashes, h2)
+    for i, c in enumerate(counts):
+        assert entries[i, :c].tobytes() == e2[i, :c].tobytes()
+    a = plan_batch(buf, offs, [len(d) for d in datas], walked=buf._bj_walk)
+    b_ = plan_batch(buf, offs, [len(d) for d in datas])
+    assert a.scans.tobytes() == b_.scans.tobytes() and np.array_equal(a.tile_scan, b_.tile_scan)
+    assert np.array_equal(a.lut, b_.lut) and [vars(g) for g in a.groups] == [vars(g) for g in b_.groups]
