@@ -81,6 +81,7 @@ static int walk_one(const uint8_t* d, uint64_t n, bj_host_entry* out, int max_en
             pos += 2;  // the reference advances by 2, not by the segment length (:476-477)
         } else if (m == 0xDA) {
             pos += size;
+            if (pos > n) pos = n;  // declared SOS length past EOF: empty run; parser.py raises CorruptedJpeg for it
             if (k >= max_entries) return -2;
             uint64_t e = bj_host_find_marker(d, n, pos);
             out[k++] = bj_host_entry{pos, e, 0x100, 0};

@@ -213,12 +213,12 @@ class FastPlan:
                 try:
                     tpl = _Template(parse_jpeg(data))
                 except JpegError as e:
-                    tpl = e
+                    tpl = (type(e), str(e))          # cache class + message, not the instance (no traceback growth)
                 if len(cache) > 4096:
                     cache.clear()
                 cache[u] = tpl
-            if isinstance(tpl, Exception):
-                raise tpl
+            if isinstance(tpl, tuple):
+                raise tpl[0](f"File {i0}: {tpl[1]}")
             templates.append(tpl)
         tid = inv.reshape(n).astype(np.int64)
         if (np.array([t.nscan for t in templates], dtype=np.int64)[tid] != nrun).any():
@@ -228,6 +228,8 @@ class FastPlan:
         run_base = np.concatenate(([0], np.cumsum(nrun)[:-1])) if n else np.zeros(0, np.int64)
         self.parsed = LazyParsed(templates, tid, run_start, run_end, run_base, sizes)
         self.any_progressive = any(t.parsed.progressive for t in templates)
+        from .pipeline import covers_all_components
+        self.needs_zero = self.any_progressive or any(not covers_all_components(t.parsed) for t in templates)
         # ---- geometry ----------------------------------------------------------------------------------
         g = FastGeometry()
         g.parsed = self.parsed
@@ -293,6 +295,10 @@ class FastPlan:
         recs = t_recs[flat_t].copy()
         raw_off = offsets[img] + rstart
         raw_len = rend - rstart
+        if len(recs) and ((raw_len < 0).any() or (raw_off < 0).any() or (raw_off + raw_len > self.raw_bytes).any()):
+            from .errors import CorruptedJpeg
+            bad = int(img[np.flatnonzero((raw_len < 0) | (raw_off < 0) | (raw_off + raw_len > self.raw_bytes))[0]])
+            raise CorruptedJpeg(f"File {bad}: entropy-coded segment lies outside the file.")
         n_streams = recs["n_streams"].astype(np.int64)
         n_sub_max = -(-(raw_len * 8) // SUBSEQ_BITS) + n_streams
         n_tiles = np.maximum(1, -(-((raw_off & 15) + raw_len) // UNSTUFF_TILE))

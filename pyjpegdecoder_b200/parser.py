@@ -234,6 +234,10 @@ def parse_jpeg(data: bytes) -> ParsedJpeg:
                 t = 1 + 2 * ns
                 ss, se, ah, al = seg[t], seg[t + 1], seg[t + 2] >> 4, seg[t + 2] & 15
             pos += size
+            if pos > n:
+                # a declared SOS length that points past the end of the file would give the scan a negative byte
+                # range (the reference dies with an IndexError in its bit reader, :654-695)
+                raise CorruptedJpeg("Start of scan segment extends past the end of the file.")
             if p.height == 0:                                       # DNL lookup (:575-581)
                 d = find(_DNL, pos)
                 if d < 0 or d + 6 > n:
@@ -248,6 +252,8 @@ def parse_jpeg(data: bytes) -> ParsedJpeg:
                       ac_specs=tuple(huff.get(0x10 | t_) for t_ in ta))
             _classify_scan(p, sc)
             sc.data_end = find_segment_end(data, pos)
+            if sc.data_end < sc.data_start:
+                raise CorruptedJpeg("Entropy-coded segment has a negative length.")
             pos = sc.data_end
             p.scans.append(sc)
         else:
@@ -269,6 +275,8 @@ def _set_geometry(p: ParsedJpeg) -> None:
             raise CorruptedJpeg("Sampling factors cannot be zero.")
     p.hmax = max(c.h for c in p.components)
     p.vmax = max(c.v for c in p.components)
+    if sum(c.h * c.v for c in p.components) > 10:
+        raise CorruptedJpeg("More than 10 blocks per MCU.")
     kinds = set()
     for c in p.components:
         if p.hmax % c.h or p.vmax % c.v or p.hmax // c.h > 2 or p.vmax // c.v > 2 or c.h > 2 or c.v > 2:

@@ -106,6 +106,7 @@ class BatchPlan:
         n_scans = sum(len(p.scans) for p in self.parsed)
         self.scans = np.zeros(n_scans, dtype=SCAN_DTYPE)
         self.any_progressive = any(p.progressive for p in self.parsed)
+        self.needs_zero = self.any_progressive or any(not covers_all_components(p) for p in self.parsed)
         lut_parts: List[np.ndarray] = []
         lut_cache: Dict[tuple, Tuple[int, int, list, list]] = {}
         lut_size = 0
@@ -125,6 +126,8 @@ class BatchPlan:
             rec = self.scans[k]
             raw_off = offsets[i] + sc.data_start
             raw_len = sc.data_end - sc.data_start
+            if raw_len < 0 or raw_off < 0 or raw_off + raw_len > raw_bytes:
+                raise CorruptedJpeg(f"File {i}: entropy-coded segment lies outside the file.")
             n_mcu = sc.mcus_x * sc.mcus_y
             ri = sc.ri if sc.ri > 0 else n_mcu
             n_streams = -(-n_mcu // ri)
@@ -138,6 +141,8 @@ class BatchPlan:
             lut_off, lut_len, dc_off, ac_off = lut_cache[key]
             s0 = slot0_of(p)
             slot = 0
+            if sum((p.components[ci].h * p.components[ci].v if len(sc.comps) > 1 else 1) for ci in sc.comps) > MAX_SLOTS:
+                raise CorruptedJpeg("More than 10 blocks per MCU.")
             for kk, ci in enumerate(sc.comps):
                 c = p.components[ci]
                 nb = c.h * c.v if len(sc.comps) > 1 else 1
@@ -186,6 +191,16 @@ class BatchPlan:
         self.lut = np.concatenate(lut_parts).astype(np.uint32)
         self.max_chain = max((-(-g.max_sub // ENTROPY_THREADS)) * g.count for g in self.groups
                              if g.mode in (0, 1, 3)) if any(g.mode in (0, 1, 3) for g in self.groups) else 1
+
+
+def covers_all_components(p: ParsedJpeg) -> bool:
+    """True if the scans of a baseline image write every coefficient block (the write kernel stores whole blocks,
+    so the coefficient buffer then needs no memset).  A truncated non-interleaved file leaves components unscanned:
+    the reference keeps their planes at zero (:627-632), so the buffer must be cleared."""
+    seen = set()
+    for sc in p.scans:
+        seen.update(sc.comps)
+    return len(seen) == p.ncomp
 
 
 _PINNED_POOL: Dict[object, torch.Tensor] = {}     # keyed slots (one owner each, e.g. loader._Uploader)
@@ -426,7 +441,7 @@ class DevicePipeline:
             events.setdefault(name, []).append((a, b))
 
         with torch.cuda.device(self.dev), torch.cuda.stream(s):
-            if plan.any_progressive:
+            if getattr(plan, "needs_zero", plan.any_progressive):
                 self.coef.zero_()
             self.err.zero_()
             timed("unstuff", lambda: _native.check(L.bj_unstuff(

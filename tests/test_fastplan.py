@@ -112,3 +112,59 @@ def test_pack_with_walk_gives_the_same_walk_and_plan():
     b_ = plan_batch(buf, offs, [len(d) for d in datas])
     assert a.scans.tobytes() == b_.scans.tobytes() and np.array_equal(a.tile_scan, b_.tile_scan)
     assert np.array_equal(a.lut, b_.lut) and [vars(g) for g in a.groups] == [vars(g) for g in b_.groups]
+
+
+# ---- malformed headers: wrapped scan lengths must never reach the device ------------------------
+def _crafted_sos_past_eof():
+    """A valid small baseline file whose SOS length field is patched to point far past EOF."""
+    from pathlib import Path
+    data = bytearray((Path(__file__).parent / "golden" / "cases" / "base_120x88_ss2.jpg").read_bytes())
+    sos = data.find(b"\xff\xda")
+    data[sos + 2:sos + 4] = (0xFFF0).to_bytes(2, "big")
+    return bytes(data[:sos + 40])
+
+
+def test_sos_length_past_eof_is_corrupted_jpeg_in_both_planners():
+    import numpy as np
+    import pytest
+    from pyjpegdecoder_b200.errors import CorruptedJpeg
+    from pyjpegdecoder_b200.fastplan import FastPlan
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    bad = _crafted_sos_past_eof()
+    with pytest.raises(CorruptedJpeg):
+        parse_jpeg(bad)
+    files = [bad] * 8
+    offs, total = [], 0
+    for f in files:
+        offs.append(total)
+        total += (len(f) + 15) & ~15
+    raw = np.zeros(total + 64, np.uint8)
+    for f, o in zip(files, offs):
+        raw[o:o + len(f)] = np.frombuffer(f, np.uint8)
+    with pytest.raises(CorruptedJpeg):
+        FastPlan(raw, offs, [len(f) for f in files])
+    with pytest.raises(CorruptedJpeg):          # cached (type, message), raised again as a fresh instance
+        FastPlan(raw, offs, [len(f) for f in files])
+
+
+def test_too_many_blocks_per_mcu_is_a_jpeg_error():
+    import pytest
+    from pathlib import Path
+    from pyjpegdecoder_b200.errors import JpegError
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    data = bytearray((Path(__file__).parent / "golden" / "cases" / "base_120x88_ss2.jpg").read_bytes())
+    sof = data.find(b"\xff\xc0")
+    for i in range(3):                       # 2x2 sampling on every component: 12 blocks per MCU
+        data[sof + 4 + 6 + 3 * i + 1] = 0x22
+    with pytest.raises(JpegError):
+        parse_jpeg(bytes(data))
+
+
+def test_unscanned_components_force_a_zeroed_coefficient_buffer():
+    from pathlib import Path
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    from pyjpegdecoder_b200.pipeline import covers_all_components
+    p = parse_jpeg((Path(__file__).parent / "golden" / "cases" / "base_120x88_ss2.jpg").read_bytes())
+    assert covers_all_components(p)
+    p.scans[0].comps = (0,)
+    assert not covers_all_components(p)
