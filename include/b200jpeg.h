@@ -275,6 +275,7 @@ void bj_host_pack_walk_keys(const uint8_t* const* src, const uint64_t* size, con
  *
  *   images      device array of n_images bj_image
  *   in          coefficient buffer (BJ_IN_COEF) or sample buffer (BJ_IN_SAMPLES)
+ *   total_blocks number of 128-byte blocks in `in` (bounds of the TMA tensor map over the coefficient buffer)
  *   qtabs       int16 quantisation tables, 64 entries each, zig-zag order as in the DQT segment
  *   idct_table_t 4096 doubles [u][v][x][y]: the reference's InverseDCT.idct_table (:1541-1553,
  *               indexed [x][y][u][v] there) TRANSPOSED so that the 64 output samples of one (u,v)
@@ -291,7 +292,7 @@ void bj_host_pack_walk_keys(const uint8_t* const* src, const uint64_t* size, con
  *   stats       optional device uint32[4]: [0] blocks recomputed exactly, [1] pixels recomputed exactly
  */
 bj_status bj_pixels(const bj_image* images, int n_images, int max_strips, const void* in, int in_kind,
-                    const int16_t* qtabs, const double* idct_table_t, void* out, int out_kind,
+                    uint64_t total_blocks, const int16_t* qtabs, const double* idct_table_t, void* out, int out_kind,
                     uint32_t layout_mask, uint32_t* stats, void* stream);
 
 #ifdef __cplusplus

@@ -51,7 +51,7 @@ def lib():
     L.bj_sizeof.restype = c_int
     L.bj_sizeof.argtypes = [c_int]
     L.bj_pixels.restype = c_int
-    L.bj_pixels.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+    L.bj_pixels.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_int,
                             ctypes.c_uint32, c_void_p, c_void_p]
     if L.bj_sizeof(0) != IMAGE_DTYPE.itemsize:
         raise NativeLibraryError("struct bj_image layout mismatch between Python and libb200jpeg.so")

@@ -447,9 +447,12 @@ bj_status bj_set_cuda_error(cudaError_t e, const char* where) {
 bj_status bj_pixels_fast_launch(const bj_image* images, int n_images, int max_strips, const int16_t* coef,
                                 const int16_t* qtabs, const double* tabT, uint8_t* out, uint32_t layout_mask,
                                 uint32_t* stats, void* stream);
+bj_status bj_pixels_420_launch(const bj_image* images, int n_images, int max_strips, const int16_t* coef,
+                               uint64_t total_blocks, const int16_t* qtabs, const double* tabT, uint8_t* out,
+                               uint32_t* stats, void* stream);
 
 bj_status bj_pixels(const bj_image* images, int n_images, int max_strips, const void* in, int in_kind,
-                    const int16_t* qtabs, const double* idct_table_t, void* out, int out_kind,
+                    uint64_t total_blocks, const int16_t* qtabs, const double* idct_table_t, void* out, int out_kind,
                     uint32_t layout_mask, uint32_t* stats, void* stream) {
     if (!images || n_images <= 0 || max_strips <= 0 || !in || !qtabs || !idct_table_t || !out) return BJ_E_ARG;
     if (n_images > 65535) return BJ_E_ARG;
@@ -458,9 +461,14 @@ bj_status bj_pixels(const bj_image* images, int n_images, int max_strips, const 
     static_assert(sizeof(bj_image) == 72, "bj_image layout");
     int only_generic = 0;
     if (in_kind == BJ_IN_COEF && out_kind == BJ_OUT_RGB && layout_mask != 0) {
-        if (layout_mask & ~1u) {
+        if (layout_mask & (1u << BJ_LAYOUT_420)) {
+            bj_status st = bj_pixels_420_launch(images, n_images, max_strips, (const int16_t*)in, total_blocks, qtabs,
+                                                idct_table_t, (uint8_t*)out, stats, stream);
+            if (st != BJ_OK) return st;
+        }
+        if (layout_mask & ~(1u | (1u << BJ_LAYOUT_420))) {
             bj_status st = bj_pixels_fast_launch(images, n_images, max_strips, (const int16_t*)in, qtabs, idct_table_t,
-                                                 (uint8_t*)out, layout_mask, stats, stream);
+                                                 (uint8_t*)out, layout_mask & ~(1u << BJ_LAYOUT_420), stats, stream);
             if (st != BJ_OK) return st;
         }
         if (!(layout_mask & 1u)) return BJ_OK;

@@ -562,9 +562,10 @@ cudaError_t launch(const bj_image* images, int n_images, int max_strips, const i
 
 // MCUs per CTA of the specialised kernel for a layout (0 for the generic layout); the host sizes the
 // grid with it (strips_per_row = ceil(mcus_x / strip)).
+extern "C" int bj_pixels_420_strip(void);
 extern "C" int bj_pixels_fast_strip(int layout) {
     switch (layout) {
-        case BJ_LAYOUT_420: return Lay<2, 2, 3>::STRIP;
+        case BJ_LAYOUT_420: return bj_pixels_420_strip();  // bj_pixels_mma.cu
         case BJ_LAYOUT_422: return Lay<2, 1, 3>::STRIP;
         case BJ_LAYOUT_440: return Lay<1, 2, 3>::STRIP;
         case BJ_LAYOUT_444: return Lay<1, 1, 3>::STRIP;

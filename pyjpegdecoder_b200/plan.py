@@ -66,9 +66,9 @@ def layout_of(p: ParsedJpeg) -> int:
             (1, 1): _native.LAYOUT_444}.get((c0.h, c0.v), _native.LAYOUT_GENERIC)
 
 
-# MCUs per CTA of the layout-specialised kernel: 6 warps x (32 // blocks_per_mcu) MCUs
-# (must equal Lay<...>::STRIP in csrc/bj_pixels_fast.cu; checked against bj_pixels_fast_strip() at load)
-FAST_STRIP = {_native.LAYOUT_420: 30, _native.LAYOUT_422: 48, _native.LAYOUT_440: 48, _native.LAYOUT_444: 60,
+# MCUs per CTA of the layout-specialised kernels: 4:2:0 -> 32 (csrc/bj_pixels_mma.cu), the others 6 warps x
+# (32 // blocks_per_mcu) MCUs (Lay<...>::STRIP in csrc/bj_pixels_fast.cu); checked against bj_pixels_fast_strip() at load
+FAST_STRIP = {_native.LAYOUT_420: 32, _native.LAYOUT_422: 48, _native.LAYOUT_440: 48, _native.LAYOUT_444: 60,
               _native.LAYOUT_GRAY: 192}
 
 

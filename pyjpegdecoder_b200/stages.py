@@ -62,7 +62,7 @@ def run_pixels(dg: DeviceGeometry, inp: torch.Tensor, in_kind: int, out_kind: in
             out = torch.zeros(max(g.out_bytes, 16), dtype=torch.int16, device=dg.device)
     s = stream if stream is not None else torch.cuda.current_stream(dg.device)
     with torch.cuda.device(dg.device):
-        st = L.bj_pixels(dg.images.data_ptr(), len(g.parsed), g.max_strips, inp.data_ptr(), in_kind,
+        st = L.bj_pixels(dg.images.data_ptr(), len(g.parsed), g.max_strips, inp.data_ptr(), in_kind, g.total_blocks,
                          dg.qtabs.data_ptr(), dg.table.data_ptr(), out.data_ptr(), out_kind,
                          0 if force_generic else g.layout_mask,
                          stats.data_ptr() if stats is not None else None, s.cuda_stream)

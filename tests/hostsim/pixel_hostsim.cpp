@@ -32,6 +32,54 @@ void hs_idct_blocks(const int32_t* blocks, int n, int16_t* out, uint8_t* flagged
     }
 }
 
+// The packed fast path of csrc/bj_pixels_mma.cu (block_idct): DC peeling, packed IDCT (the host build runs the
+// same fmaf / + / * sequence lane by lane), magic-add rounding, tie test.  blocks: n x 64 dequantised coefficients
+// in natural order [v*8+u]; lo4 != 0 runs the 4x4 low-frequency variant (coefficients outside the corner must be 0).
+void hs_idct_blocks_packed(const int32_t* blocks, int n, int lo4, int16_t* out, uint8_t* flagged, float* max_dist,
+                           float* thresholds, double* raw) {
+    using bj::F2;
+    for (int b = 0; b < n; b++) {
+        F2 P[8][4];
+        float Sw = 0.f;
+        for (int k = 0; k < 64; k++) {
+            const float x = (float)blocks[b * 64 + k];
+            const int v = k >> 3, u = k & 7;
+            if (u & 1) P[v][u >> 1].y = x; else P[v][u >> 1].x = x;
+            if (k) Sw = fmaf(fabsf(x), bj::idct_err_weight(v, u), Sw);
+        }
+        const float dc_abs = fabsf(P[0][0].x);
+        const float S = Sw * (1.0f / BJ_IDCT_W_MIN);
+        const float dc_int = bj::dc_peel(P[0][0].x);
+        const float T = fmaf(fmaf(P[0][0].x, bj::idct_err_weight(0, 0), Sw), BJ_IDCT_ERR_U, BJ_IDCT_ERR_ABS);
+        const float shift = (BJ_MAGIC + 128.0f) + dc_int;
+        F2 W[4][8];
+        float maxd;
+        if (lo4) bj::idct8x8_round_packed<true>(P, shift, W, maxd);
+        else bj::idct8x8_round_packed<false>(P, shift, W, maxd);
+        for (int yp = 0; yp < 4; yp++)
+            for (int x = 0; x < 8; x++) {
+                uint32_t b0, b1;
+                memcpy(&b0, &W[yp][x].x, 4);
+                memcpy(&b1, &W[yp][x].y, 4);
+                out[b * 64 + (2 * yp) * 8 + x] = (int16_t)(b0 & 0xffffu);
+                out[b * 64 + (2 * yp + 1) * 8 + x] = (int16_t)(b1 & 0xffffu);
+            }
+        flagged[b] = (maxd > 0.5f - T) || (S + dc_abs > 32767.0f);
+        if (max_dist) max_dist[b] = maxd;
+        if (thresholds) thresholds[b] = T;
+        if (raw) {   // the fp32 values before rounding (error probe): v = (W - shift) + (v - rint(v)) is not recoverable
+                     // exactly from W, so run the transform again without the rounding step
+            F2 R[4][8];
+            if (lo4) bj::idct8x8_packed<true>(P, R); else bj::idct8x8_packed<false>(P, R);
+            for (int yp = 0; yp < 4; yp++)
+                for (int x = 0; x < 8; x++) {
+                    raw[b * 64 + (2 * yp) * 8 + x] = (double)R[yp][x].x + (double)dc_int;
+                    raw[b * 64 + (2 * yp + 1) * 8 + x] = (double)R[yp][x].y + (double)dc_int;
+                }
+        }
+    }
+}
+
 // weights of kind (rh, rv) for MCU pixel (b, a): w[b*16+a][4] = w00,w10,w01,w11 and cell i,j
 void hs_weights(int rh, int rv, int32_t* w, int32_t* cell) {
     for (int b = 0; b < 16; b++)

@@ -78,6 +78,64 @@ def test_idct_fast_path_never_accepts_a_wrong_sample(hs, mode):
         assert flagged.mean() < 0.2   # and the exact path stays rare on ordinary content
 
 
+def _idct_packed(hs, blocks_nat, lo4=False):
+    n = blocks_nat.shape[0]
+    b = np.ascontiguousarray(blocks_nat, dtype=np.int32)
+    out = np.empty((n, 64), np.int16)
+    flg = np.empty(n, np.uint8)
+    dist = np.empty(n, np.float32)
+    hs.hs_idct_blocks_packed(b.ctypes.data_as(ctypes.c_void_p), n, int(lo4), out.ctypes.data_as(ctypes.c_void_p),
+                             flg.ctypes.data_as(ctypes.c_void_p), dist.ctypes.data_as(ctypes.c_void_p), None, None)
+    return out, flg.astype(bool), dist
+
+
+@pytest.mark.parametrize("mode", ["dense", "sparse", "dc_only", "ties", "large"])
+def test_packed_idct_never_accepts_a_wrong_sample(hs, mode):
+    """The FFMA2-shaped fast path of csrc/bj_pixels_mma.cu (DC peeling + packed IDCT + magic-add rounding)."""
+    rng = np.random.default_rng((hash(mode) & 0xFFFF) + 1)
+    b = _random_blocks(rng, 1500, mode)
+    fast, flagged, _ = _idct_packed(hs, b)
+    want = _oracle_idct(b)
+    ok = ~flagged
+    assert np.array_equal(fast[ok], want[ok])
+    if mode == "ties":
+        assert flagged.all()
+    if mode == "sparse":
+        assert flagged.mean() < 0.2
+    if mode == "large":
+        assert flagged.all()          # products beyond int16 (:869 wraps) always go to the exact path
+
+
+def test_packed_idct_low_frequency_variant(hs):
+    """Blocks confined to the 4x4 low-frequency corner: the LO4 variant must agree with the oracle (where accepted)
+    and with the dense variant's decisions on the same blocks."""
+    rng = np.random.default_rng(77)
+    n = 3000
+    b = np.zeros((n, 8, 8), np.int32)
+    b[:, :4, :4] = rng.integers(-200, 200, (n, 4, 4)) * (rng.random((n, 4, 4)) < 0.5)
+    b[:, 0, 0] = rng.integers(-1024, 1024, n)
+    b = b.reshape(n, 64)
+    lo, flo, _ = _idct_packed(hs, b, lo4=True)
+    want = _oracle_idct(b)
+    assert np.array_equal(lo[~flo], want[~flo])
+    de, fde, _ = _idct_packed(hs, b, lo4=False)
+    assert np.array_equal(de[~fde], want[~fde])
+    assert flo.mean() < 0.1
+
+
+def test_dc_peeling_lowers_the_exact_path_rate(hs):
+    """Same blocks through the scalar fast path (tie threshold grows with |DC|) and the packed one (DC peeled)."""
+    rng = np.random.default_rng(9)
+    n = 20000
+    b = np.zeros((n, 64), np.int32)
+    mask = rng.random((n, 64)) < 0.2
+    b[mask] = rng.integers(-60, 60, mask.sum())
+    b[:, 0] = rng.integers(-1000, 1000, n)
+    _, f_old, _ = _idct(hs, b)
+    _, f_new, _ = _idct_packed(hs, b)
+    assert f_new.mean() < 0.8 * f_old.mean()
+
+
 def test_idct_fast_path_on_real_coefficients(hs):
     """Dequantised blocks of real files: fast path result == oracle wherever it is accepted."""
     from pyjpegdecoder_b200.parser import parse_jpeg
@@ -96,6 +154,8 @@ def test_idct_fast_path_on_real_coefficients(hs):
             fast, flagged, _ = _idct(hs, nat)
             want = _oracle_idct(nat)
             assert np.array_equal(fast[~flagged], want[~flagged]), name
+            fast2, flagged2, _ = _idct_packed(hs, nat)
+            assert np.array_equal(fast2[~flagged2], want[~flagged2]), name
 
 
 @pytest.mark.parametrize("kind,key", [((2, 2), "w_8x8_16x16"), ((2, 1), "w_8x8_16x8"), ((1, 2), "w_8x8_8x16")])
