@@ -51,7 +51,9 @@ constexpr int OFF_COEF = 0;                    // 24576: TMA tile [192][128 B], 
 constexpr int OFF_Y = OFF_COEF + 24576;        // 16384: luma samples int16 [32 MCUs][4][8][8]
 constexpr int OFF_C = OFF_Y + 16384;           //  8192: chroma samples f16 (int16 for wide blocks) [32 MCUs][8 rows][4 column pairs][Cb, Cr]
 constexpr int OFF_Q = OFF_C + 8192;            //   768: quantisation tables as float [3][64]
-constexpr int OFF_MISC = OFF_Q + 768;          //    32: mbarrier, wide masks
+constexpr int OFF_BASIS = OFF_Q + 768;         //   512: 1-D IDCT basis in double precision (exact recompute)
+constexpr int OFF_NATZZ = OFF_BASIS + 512;     //    64: reference flat index u*8+v -> zig-zag index (exact recompute)
+constexpr int OFF_MISC = OFF_NATZZ + 64;       //    32: mbarrier, wide masks
 constexpr int SMEM_USED = OFF_MISC + 32;
 constexpr int SMEM_BYTES = SMEM_USED;
 
@@ -128,7 +130,20 @@ struct Tiles {
     __device__ __forceinline__ unsigned char* stage(int row) const { return base + OFF_COEF + row * kRowBytes; }
     __device__ __forceinline__ const float* qf() const { return reinterpret_cast<const float*>(base + OFF_Q); }
     __device__ __forceinline__ Misc* misc() const { return reinterpret_cast<Misc*>(base + OFF_MISC); }
+    __device__ __forceinline__ const double* basis() const { return reinterpret_cast<const double*>(base + OFF_BASIS); }
+    __device__ __forceinline__ const uint8_t* nat_zz() const { return base + OFF_NATZZ; }
 };
+
+// Store two exactly recomputed samples (x0, y) and (x1, y) of a block: luma int16, chroma f16 (int16 when wide).
+// Out of line and shared by both exact routines: cold code, kept small.
+__device__ __noinline__ void store_exact_pair(const Tiles t, int m, int s, int comp, bool as_int16, int y, int x0, int v0, int x1, int v1) {
+    unsigned char* p0 = comp == 0 ? t.yrow(m, s, y) + 2 * x0 : t.cpair(m, comp - 1, y, x0 >> 1) + 2 * (x0 & 1);
+    unsigned char* p1 = comp == 0 ? t.yrow(m, s, y) + 2 * x1 : t.cpair(m, comp - 1, y, x1 >> 1) + 2 * (x1 & 1);
+    const bool i16 = comp == 0 || as_int16;
+    // |v| <= 2048 in a chroma block that is not wide: exact in f16
+    *reinterpret_cast<uint16_t*>(p0) = i16 ? (uint16_t)v0 : __half_as_ushort(__int2half_rn(v0));
+    *reinterpret_cast<uint16_t*>(p1) = i16 ? (uint16_t)v1 : __half_as_ushort(__int2half_rn(v1));
+}
 
 // reference flat index u*8+v -> zig-zag index (zagzig, jpeg_decoder.py:1672-1681, inverted)
 __constant__ uint8_t c_nat_zz[64] = {0, 2, 3, 9, 10, 20, 21, 35, 1, 4, 8, 11, 19, 22, 34, 36, 5, 7, 12, 18, 23, 33,
@@ -175,18 +190,7 @@ __device__ __noinline__ void recompute_block_exact(const Tiles t, int R, int m, 
                           __dadd_rn(__dadd_rn(r1[4], r1[5]), __dadd_rn(r1[6], r1[7])));
     const int x0 = lane >> 3, y0 = lane & 7, x1 = x0 + 4;
     const int v0 = (int16_t)(__double2int_rn(s0)) + 128, v1 = (int16_t)(__double2int_rn(s1)) + 128;
-    if (comp == 0) {
-        int16_t* row = reinterpret_cast<int16_t*>(t.yrow(m, s, y0));
-        row[x0] = (int16_t)v0;
-        row[x1] = (int16_t)v1;
-    } else if (as_int16) {
-        reinterpret_cast<int16_t*>(t.cpair(m, comp - 1, y0, x0 >> 1))[x0 & 1] = (int16_t)v0;
-        reinterpret_cast<int16_t*>(t.cpair(m, comp - 1, y0, x1 >> 1))[x1 & 1] = (int16_t)v1;
-    } else {
-        // |v| <= 2048 in a block that is not wide: exact
-        reinterpret_cast<__half*>(t.cpair(m, comp - 1, y0, x0 >> 1))[x0 & 1] = __int2half_rn(v0);
-        reinterpret_cast<__half*>(t.cpair(m, comp - 1, y0, x1 >> 1))[x1 & 1] = __int2half_rn(v1);
-    }
+    store_exact_pair(t, m, s, comp, as_int16, y0, x0, v0, x1, v1);
 }
 
 // c(n, k) = a_k cos((2n + 1) k pi / 16), a_0 = 1 / (2 sqrt 2), a_k = 1/2: the 1-D inverse DCT basis in double precision
@@ -212,27 +216,30 @@ __device__ const double g_idct_basis[64] = {
 __device__ __noinline__ bool recompute_block_sep(const Tiles t, int R, int m, int s, int comp, bool as_int16, float sum_abs, int lane) {
     const float* qf = t.qf() + comp * 64;
     const int a = lane >> 3, b = lane & 7;
-    const int k0 = c_nat_zz[lane], k1 = c_nat_zz[lane + 32];
+    const int k0 = t.nat_zz()[lane], k1 = t.nat_zz()[lane + 32];
+    const double* basis = t.basis();
     const int c0 = *reinterpret_cast<const int16_t*>(t.coef_chunk(R, k0 >> 3) + ((k0 & 7) << 1));
     const int c1 = *reinterpret_cast<const int16_t*>(t.coef_chunk(R, k1 >> 3) + ((k1 & 7) << 1));
     const int p0 = (int16_t)(c0 * (int)qf[k0]), p1 = (int16_t)(c1 * (int)qf[k1]);  // int16 product wraps (:869)
+    // (rolled loops: this code runs for one block in ~270 and is fetched cold every time -- its instruction
+    // footprint, not its instruction count, is what the rest of the CTA waits for)
     // pass 1: contract over v (vertical frequency) for y = b
     double h0 = 0.0, h1 = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int v = 0; v < 8; v++) {
-        const double cv = g_idct_basis[b * 8 + v];
+        const double cv = basis[b * 8 + v];
         h0 = fma((double)__shfl_sync(0xffffffffu, p0, a * 8 + v), cv, h0);
         h1 = fma((double)__shfl_sync(0xffffffffu, p1, a * 8 + v), cv, h1);
     }
     // pass 2: contract over u (horizontal frequency) for x = a and a + 4
     double s0 = 0.0, s1 = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int ap = 0; ap < 4; ap++) {
         const double lo = __shfl_sync(0xffffffffu, h0, ap * 8 + b), hi = __shfl_sync(0xffffffffu, h1, ap * 8 + b);  // u = ap, ap + 4
-        s0 = fma(lo, g_idct_basis[a * 8 + ap], s0);
-        s0 = fma(hi, g_idct_basis[a * 8 + ap + 4], s0);
-        s1 = fma(lo, g_idct_basis[(a + 4) * 8 + ap], s1);
-        s1 = fma(hi, g_idct_basis[(a + 4) * 8 + ap + 4], s1);
+        s0 = fma(lo, basis[a * 8 + ap], s0);
+        s0 = fma(hi, basis[a * 8 + ap + 4], s0);
+        s1 = fma(lo, basis[(a + 4) * 8 + ap], s1);
+        s1 = fma(hi, basis[(a + 4) * 8 + ap + 4], s1);
     }
     const double r0 = rint(s0), r1 = rint(s1);
     const double guard = 1e-13 * ((double)sum_abs + 8.0);
@@ -240,17 +247,7 @@ __device__ __noinline__ bool recompute_block_sep(const Tiles t, int R, int m, in
     if (__any_sync(0xffffffffu, unsure)) return false;
     const int x0 = a, y0 = b, x1 = a + 4;
     const int v0 = (int16_t)(__double2int_rn(s0)) + 128, v1 = (int16_t)(__double2int_rn(s1)) + 128;
-    if (comp == 0) {
-        int16_t* row = reinterpret_cast<int16_t*>(t.yrow(m, s, y0));
-        row[x0] = (int16_t)v0;
-        row[x1] = (int16_t)v1;
-    } else if (as_int16) {
-        reinterpret_cast<int16_t*>(t.cpair(m, comp - 1, y0, x0 >> 1))[x0 & 1] = (int16_t)v0;
-        reinterpret_cast<int16_t*>(t.cpair(m, comp - 1, y0, x1 >> 1))[x1 & 1] = (int16_t)v1;
-    } else {
-        reinterpret_cast<__half*>(t.cpair(m, comp - 1, y0, x0 >> 1))[x0 & 1] = __int2half_rn(v0);
-        reinterpret_cast<__half*>(t.cpair(m, comp - 1, y0, x1 >> 1))[x1 & 1] = __int2half_rn(v1);
-    }
+    store_exact_pair(t, m, s, comp, as_int16, y0, x0, v0, x1, v1);
     return true;
 }
 
@@ -502,6 +499,10 @@ bj_pixels_420_kernel(const __grid_constant__ CUtensorMap tmap, const bj_image* _
     for (int i = tid; i < 192; i += kThreads) {
         float* qf = reinterpret_cast<float*>(t.base + OFF_Q);
         qf[i] = (float)qtabs[(size_t)__ldg(&gi->qtab[i >> 6]) * 64 + (i & 63)];
+    }
+    if (tid < 64) {   // tables of the exact recompute: shared-memory copies keep its (serial) latency short
+        reinterpret_cast<double*>(t.base + OFF_BASIS)[tid] = g_idct_basis[tid];
+        t.base[OFF_NATZZ + tid] = c_nat_zz[tid];
     }
     __syncthreads();
     mbar_wait(&misc->mbar, 0);
