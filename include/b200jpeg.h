@@ -90,7 +90,9 @@ typedef struct bj_image {
  * SUBSEQUENCES of BJ_SUBSEQ_BITS bits that are decoded speculatively and then stitched together
  * (self-synchronising Huffman decode), see DESIGN.md.
  * ------------------------------------------------------------------------------------------- */
-#define BJ_SUBSEQ_BITS 1024
+#ifndef BJ_SUBSEQ_BITS
+#define BJ_SUBSEQ_BITS 4096   /* bj_sizeof_entropy(3) reports the value the library was built with */
+#endif
 #ifndef BJ_ENTROPY_THREADS
 #define BJ_ENTROPY_THREADS 128 /* subsequences per CTA */
 #endif
@@ -223,7 +225,7 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
 
 int bj_version(void);
 int bj_sizeof(int what);         /* 0: sizeof(bj_image) -- lets a binding verify its struct mirrors */
-int bj_sizeof_entropy(int what); /* 1: sizeof(bj_scan), 2: sizeof(bj_entropy_buffers) */
+int bj_sizeof_entropy(int what); /* 1: sizeof(bj_scan), 2: sizeof(bj_entropy_buffers), 3: BJ_SUBSEQ_BITS */
 int bj_pixels_fast_strip(int layout); /* MCUs per CTA the specialised pixel kernel uses for BJ_LAYOUT_* (0: generic) */
 const char* bj_last_cuda_error(void);
 

@@ -788,7 +788,9 @@ static_assert(sizeof(bj_scan) == 144, "bj_scan layout");
 static_assert(offsetof(bj_scan, raw_len) == 16 && offsetof(bj_scan, tile0) == 60 && offsetof(bj_scan, frame_mcus_x) == 64 &&
               offsetof(bj_scan, slot_frame) == 78 && offsetof(bj_scan, slot_comp) == 88 && offsetof(bj_scan, slot_dc) == 98 &&
               offsetof(bj_scan, slot_ac) == 118 && offsetof(bj_scan, reserved) == 140, "bj_scan layout");
-int bj_sizeof_entropy(int what) { return what == 1 ? (int)sizeof(bj_scan) : what == 2 ? (int)sizeof(bj_entropy_buffers) : -1; }
+int bj_sizeof_entropy(int what) {
+    return what == 1 ? (int)sizeof(bj_scan) : what == 2 ? (int)sizeof(bj_entropy_buffers) : what == 3 ? BJ_SUBSEQ_BITS : -1;
+}
 
 bj_status bj_entropy_plan(const bj_scan* scans, int scan_first, int n_scans, const uint64_t* tile_sum,
                           const bj_entropy_buffers* bufs, void* stream) {

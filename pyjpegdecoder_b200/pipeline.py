@@ -27,7 +27,21 @@ from .parser import ParsedJpeg, Scan, parse_jpeg
 from .plan import BatchGeometry, scan_levels
 from .stages import DeviceGeometry, require_cuda, run_pixels, to_device
 
-SUBSEQ_BITS = 1024
+
+
+def _subseq_bits() -> int:
+    """BJ_SUBSEQ_BITS of the built library (bj_sizeof_entropy(3)); 1024 when the library is absent (planning only)."""
+    try:
+        L = _native.lib()
+        L.bj_sizeof_entropy.restype = ctypes.c_int
+        L.bj_sizeof_entropy.argtypes = [ctypes.c_int]
+        v = int(L.bj_sizeof_entropy(3))
+        return v if v > 0 else 1024
+    except NativeLibraryError:
+        return 1024
+
+
+SUBSEQ_BITS = _subseq_bits()
 ENTROPY_THREADS = 128
 UNSTUFF_TILE = 4096
 MAX_SLOTS = 10
