@@ -34,6 +34,10 @@ namespace {
 using namespace bj;
 
 constexpr int T = BJ_ENTROPY_THREADS;
+#ifndef BJ_WRITE_THREADS
+#define BJ_WRITE_THREADS 128
+#endif
+constexpr int TW = BJ_WRITE_THREADS;  // subsequences per CTA of write_kernel (its LUT copy is amortised over more threads)
 constexpr int S = BJ_SUBSEQ_BITS;
 constexpr int kWinWords = (T + 1) * (S / 32) + 64;  // bit window of one CTA, in 32-bit words
 constexpr int kMaxLutSmem = 12288;                  // most LUT entries ever staged in shared memory (48 KB)
@@ -62,7 +66,9 @@ struct WinSrc {
 struct GlobalSrc {
     const uint32_t* gw;
     uint32_t gn;
-    __device__ __forceinline__ uint32_t word(uint32_t i) const { return i < gn ? __ldg(gw + i) : 0xFFFFFFFFu; }
+    // clamped, not branched: the buffer ends with 64 words of slack, a valid stream never reads past them, and what a
+    // corrupt one reads there does not matter as long as it is deterministic
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return __ldg(gw + min(i, gn - 1u)); }
 };
 
 struct CtaShared {
@@ -107,6 +113,7 @@ __device__ __forceinline__ void load_scan_header(SH& sh, const bj_scan* scans, i
             sh.ctx.ac_tab[i] = sc.slot_ac[i];
             sh.ctx.slot_comp[i] = sc.slot_comp[i];
         }
+        ctx_finish(sh.ctx);
         sh.ctx.nslots = sc.nslots;
         sh.ctx.ss = sc.ss;
         sh.ctx.se = sc.se;
@@ -136,6 +143,7 @@ __device__ __forceinline__ void load_scan(SH& sh, const bj_scan* scans, int idx,
             sh.ctx.ac_tab[i] = sc.slot_ac[i];
             sh.ctx.slot_comp[i] = sc.slot_comp[i];
         }
+        ctx_finish(sh.ctx);
         sh.ctx.nslots = sc.nslots;
         sh.ctx.ss = sc.ss;
         sh.ctx.se = sc.se;
@@ -542,7 +550,7 @@ __device__ __forceinline__ size_t block_address(const bj_scan& sc, uint32_t mcu,
 }
 
 // Baseline block sink: the thread's block lives in shared memory as 8 chunks of 16 bytes, chunk c of
-// thread t at (c * T + t) * 16: conflict-free 128-bit reads when the block is flushed.
+// thread t at (c * TW + t) * 16: conflict-free 128-bit reads when the block is flushed.
 struct SmemBlockSink {
     unsigned char* base;  // buf + tid * 16
     int16_t* coef;
@@ -551,7 +559,7 @@ struct SmemBlockSink {
     uint32_t mcu_next;  // MCU of the next block to commit (0xFFFFFFFF: not known yet)
     __device__ __forceinline__ void begin() {}
     __device__ __forceinline__ void put(int z, int16_t v) {
-        *reinterpret_cast<int16_t*>(base + (z >> 3) * (T * 16) + ((z & 7) << 1)) = v;
+        *reinterpret_cast<int16_t*>(base + (z >> 3) * (TW * 16) + ((z & 7) << 1)) = v;
     }
     __device__ __forceinline__ void commit(uint32_t blk, int slot) {
         // blocks are committed in order: the MCU index is tracked instead of divided out for every block
@@ -562,7 +570,7 @@ struct SmemBlockSink {
         const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            uint4* s = reinterpret_cast<uint4*>(base + c * (T * 16));
+            uint4* s = reinterpret_cast<uint4*>(base + c * (TW * 16));
             uint4 v = *s;
             *s = zero;
             dst[c] = v;
@@ -583,7 +591,7 @@ struct GlobalCoefSink {  // progressive first scans: single coefficient stores
     }
 };
 
-__global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
+__global__ void __launch_bounds__(TW) write_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
                                                   uint32_t lut_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #if BJ_WRITE_WINDOW
@@ -592,9 +600,9 @@ __global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ sc
 #else
     CtaSharedNoWin& sh = *reinterpret_cast<CtaSharedNoWin*>(smem_raw);
 #endif
-    __shared__ __align__(16) uint32_t s_blocks[T * 32];
+    __shared__ __align__(16) uint32_t s_blocks[TW * 32];
     load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
-    const uint32_t base = blockIdx.y * T;
+    const uint32_t base = blockIdx.y * TW;
     if (base >= sh.scan_nsub) return;
     const int tid = threadIdx.x;
     const uint32_t lscan = base + tid;
@@ -602,7 +610,7 @@ __global__ void __launch_bounds__(T) write_kernel(const bj_scan* __restrict__ sc
 #if BJ_WRITE_WINDOW
     if (tid == 0) first_bit = si.own;
 #endif
-    for (int i = tid; i < T * 32; i += T) s_blocks[i] = 0u;
+    for (int i = tid; i < TW * 32; i += TW) s_blocks[i] = 0u;
     __syncthreads();
 #if BJ_WRITE_WINDOW
     load_window(sh, B, first_bit);
@@ -833,7 +841,7 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         }
         if (phases & BJ_PHASE_WRITE) {
             const size_t write_smem = BJ_WRITE_WINDOW ? smem : sizeof(CtaSharedNoWin) + sizeof(uint32_t) * lut_cap;
-            write_kernel<<<grid, T, write_smem, st>>>(scans, scan_first, *bufs, lut_cap);
+            write_kernel<<<dim3((unsigned)n_scans, (max_sub + TW - 1) / TW), TW, write_smem, st>>>(scans, scan_first, *bufs, lut_cap);
         }
     } else if (mode == BJ_MODE_DC_REFINE) {
         unsigned gx = (max_blocks + 255) / 256;

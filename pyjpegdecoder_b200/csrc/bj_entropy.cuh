@@ -47,18 +47,42 @@ BJ_HD int state_slot(uint64_t s) { return (int)((s >> 51) & 15); }
 //             byte 3 = symbol
 //   indirect: bit 7 set, bits 8..23 = offset of a 128-entry second-level table (relative to the table)
 // first level: 512 entries indexed by the next 9 bits; second level by the following 7 bits.
+#if defined(__CUDA_ARCH__)
+#define BJ_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define BJ_UNLIKELY(x) (x)
+#endif
+// byte k of a 32-bit word: one PRMT on the device
+BJ_HD uint32_t byte_of(uint32_t e, int k) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(e, 0u, 0x4440u + (uint32_t)k);
+#else
+    return (e >> (8 * k)) & 0xFFu;
+#endif
+}
 BJ_HD uint32_t lut_lookup(const uint32_t* tab, uint32_t peek16) {
     uint32_t e = tab[peek16 >> 7];
-    if (e & 0x80u) e = tab[((e >> 8) & 0xFFFFu) + (peek16 & 127u)];
+    // codes longer than 9 bits are rare symbols: a real branch, not seven predicated instructions per symbol
+    if (BJ_UNLIKELY(e & 0x80u)) e = tab[((e >> 8) & 0xFFFFu) + (peek16 & 127u)];
     return e;
 }
-BJ_HD int ent_total(uint32_t e) { return (int)(e & 0xFFu); }
-BJ_HD int ent_adv(uint32_t e) { return (int)((e >> 8) & 0xFFu); }
-BJ_HD int ent_len(uint32_t e) { return (int)((e >> 16) & 0xFFu); }
+BJ_HD int ent_total(uint32_t e) { return (int)byte_of(e, 0); }
+BJ_HD int ent_adv(uint32_t e) { return (int)byte_of(e, 1); }
+BJ_HD int ent_len(uint32_t e) { return (int)byte_of(e, 2); }
 BJ_HD int ent_sym(uint32_t e) { return (int)(e >> 24); }
 
 // EXTEND (bin_twos_complement, :1636-1646)
 BJ_HD int extend(uint32_t v, int n) { return (n == 0) ? 0 : ((v >> (n - 1)) ? (int)v : (int)v - ((1 << n) - 1)); }
+
+// EXTEND of the n (1..16) bits that follow the first `skipn` bits of the look-ahead pk, branch-free: JPEG stores a
+// negative value as the one's complement of its magnitude, so with m = all-ones when the leading bit is clear the
+// value is ((bits ^ m) >> (32 - n)) with its sign flipped by m.  n == 0 must be handled by the caller.
+BJ_HD int take_extend(uint32_t pk, int skipn, int n) {
+    const uint32_t t = pk << skipn;
+    const uint32_t m = ~(uint32_t)((int32_t)t >> 31);
+    const uint32_t w = (t ^ m) >> (32 - n);
+    return (int)((w ^ m) - m);
+}
 
 // ---- bit reader over big-endian 32-bit words -----------------------------------------------------
 // Two 32-bit words (w0 = current, w1 = next) and the number of bits of w0 already consumed: the next
@@ -76,6 +100,7 @@ template <class Src>
 struct BitReader {
     const Src* src;
     uint32_t w0, w1;  // current and next word
+    uint32_t w2;      // the word after: fetched one refill before it is needed, so its latency is off the symbol chain
     int o;            // bits of w0 consumed (0..31)
     uint32_t next;    // next word to fetch
     uint32_t rel;     // bit position relative to `base` (a stream is far below 2^32 bits)
@@ -90,7 +115,8 @@ struct BitReader {
         o = (int)(p & 31);
         w0 = src->word(w);
         w1 = src->word(w + 1);
-        next = w + 2;
+        w2 = src->word(w + 2);
+        next = w + 3;
     }
     BJ_HDM uint64_t abs_pos() const { return base + rel; }
     BJ_HDM uint32_t peek32() const { return funnel_left(w0, w1, o); }
@@ -103,7 +129,8 @@ struct BitReader {
         while (o >= 32) {
             o -= 32;
             w0 = w1;
-            w1 = src->word(next++);
+            w1 = w2;
+            w2 = src->word(next++);
         }
     }
     BJ_HDM void skip(int n) {  // n <= 32
@@ -112,7 +139,8 @@ struct BitReader {
         if (o >= 32) {
             o -= 32;
             w0 = w1;
-            w1 = src->word(next++);
+            w1 = w2;
+            w2 = src->word(next++);
         }
     }
 };
@@ -125,9 +153,13 @@ struct ScanCtx {
     uint16_t dc_tab[BJ_MAX_SLOTS];    // table offsets inside the blob
     uint16_t ac_tab[BJ_MAX_SLOTS];
     uint8_t slot_comp[BJ_MAX_SLOTS];  // slot -> DC predictor index
+    uint32_t tabs[BJ_MAX_SLOTS];      // dc_tab | ac_tab << 16 (one load per block instead of two); see ctx_finish()
     int nslots;
     int ss, se, al;
 };
+BJ_HD void ctx_finish(ScanCtx& c) {
+    for (int i = 0; i < BJ_MAX_SLOTS; i++) c.tabs[i] = (uint32_t)c.dc_tab[i] | ((uint32_t)c.ac_tab[i] << 16);
+}
 
 struct SubCount {
     uint32_t blocks;  // blocks started (baseline / DC) or block advance (AC first) in the subsequence
@@ -164,26 +196,28 @@ template <int MODE, class Src>
 BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, const uint32_t* lut, uint32_t own_rel,
                     uint32_t stop_rel, uint32_t end_rel, SubCount& cnt) {
     const int nslots = c.nslots;
-    uint32_t dct = c.dc_tab[slot], act = c.ac_tab[slot];
-    // the 1-padding of the last byte can only be met in the stream's last subsequence: everywhere else the test
-    // below is loop-invariant false (it was a tenth of this loop's instructions)
-    const bool near_end = stop_rel + 8u > end_rel;
+    uint32_t tabs = c.tabs[slot];
+    // the 1-padding of the last byte can only be met within the last 7 bits of the stream, i.e. in its last
+    // subsequence: everywhere else the test below is one compare that never fires
+    const uint32_t pad_from = (stop_rel + 8u > end_rel) ? (end_rel >= 7u ? end_rel - 7u : 0u) : 0xFFFFFFFFu;
     while (rd.rel < stop_rel) {
         const bool is_dc = (z == 0);
-        if (near_end && is_dc && end_rel - rd.rel < 8 && at_padding(rd, end_rel)) {
-            rd.rel = end_rel;
-            break;
+        if (BJ_UNLIKELY(rd.rel >= pad_from)) {
+            if (is_dc && at_padding(rd, end_rel)) {
+                rd.rel = end_rel;
+                break;
+            }
         }
         const uint32_t pk = rd.peek32();
-        const uint32_t e = lut_lookup(lut + (is_dc ? dct : act), pk >> 16);
+        const uint32_t e = lut_lookup(lut + (is_dc ? (tabs & 0xFFFFu) : (tabs >> 16)), pk >> 16);
         int adv = ent_adv(e);
         if (is_dc) {
             if (rd.rel >= own_rel) {
                 const int L = ent_len(e);
                 const int t = L ? ent_sym(e) : 0;
                 cnt.blocks++;
-                int diff = extend(t ? take_bits(pk, L, t) : 0u, t);
-                int k = c.slot_comp[slot];
+                const int diff = t ? take_extend(pk, L, t) : 0;
+                const int k = c.slot_comp[slot];
                 if (k == 0) cnt.dc[0] += diff;
                 else if (k == 1) cnt.dc[1] += diff;
                 else cnt.dc[2] += diff;
@@ -195,8 +229,7 @@ BJ_HD void sync_run(BitReader<Src>& rd, int& z, int& slot, const ScanCtx& c, con
         if (z >= 64) {
             z = 0;
             slot = (slot + 1 == nslots) ? 0 : slot + 1;
-            dct = c.dc_tab[slot];
-            act = c.ac_tab[slot];
+            tabs = c.tabs[slot];
         }
     }
 }
@@ -227,14 +260,23 @@ BJ_HD uint32_t base_write_run(BitReader<Src>& rd, int z, int slot, const ScanCtx
         }
         slot = (slot + 1 == nslots) ? 0 : slot + 1;
     }
+    // The 32 lanes of a warp walk their blocks in lock step, one block per round, and a round lasts as long as its
+    // longest block.  Luma blocks carry three times the symbols of chroma blocks, so the rounds are kept in PHASE:
+    // round k is for slot k mod nslots, a lane whose next block sits in another slot of the MCU idles until the
+    // rotation reaches it (fewer than nslots rounds, once).  From then on every lane decodes the same kind of block in
+    // every round: 4:2:0 content needs about a fifth fewer symbol iterations than with mixed rounds.
+    int phase = 0;
     while (err == 0 && rd.rel < stop_rel && blk < nblk_stream) {
+        const bool mine = (slot == phase);
+        phase = (phase + 1 == nslots) ? 0 : phase + 1;
+        if (!mine) continue;
         sink.begin();
         {
             const uint32_t pk = rd.peek32();
             uint32_t e = lut_lookup(lut + c.dc_tab[slot], pk >> 16);
             int L = ent_len(e), t = ent_sym(e);
             if (L == 0) { err |= BJ_ERR_BAD_CODE; t = 0; }
-            int diff = extend(t ? take_bits(pk, L, t) : 0u, t);
+            const int diff = t ? take_extend(pk, L, t) : 0;
             int k = c.slot_comp[slot];
             int pv;
             if (k == 0) pv = (pred[0] += diff);
@@ -244,17 +286,16 @@ BJ_HD uint32_t base_write_run(BitReader<Src>& rd, int z, int slot, const ScanCtx
             rd.skip(ent_total(e));
         }
         const uint32_t* const tab = lut + c.ac_tab[slot];
-        int zz = 1;
-        while (zz < 64) {
+        int zz = 0;  // last coefficient written
+        while (zz < 63) {
             const uint32_t pk = rd.peek32();
-            uint32_t e = lut_lookup(tab, pk >> 16);
-            int L = ent_len(e), tot = ent_total(e);
-            int s = tot - L;
-            zz += ent_adv(e) - 1;  // zero run (EOB: jumps past 63, ZRL: 15)
-            if (L == 0) { err |= BJ_ERR_BAD_CODE; zz = 64; }
-            if (s && zz < 64) sink.put(zz, (int16_t)extend(take_bits(pk, L, s), s));
+            const uint32_t e = lut_lookup(tab, pk >> 16);
+            const int L = ent_len(e), tot = ent_total(e);
+            const int s = tot - L;
+            zz += ent_adv(e);  // zero run + 1 (EOB: jumps past 63, ZRL: 16 with no value)
+            if (BJ_UNLIKELY(L == 0)) { err |= BJ_ERR_BAD_CODE; zz = 64; }
+            if (s && zz < 64) sink.put(zz, (int16_t)take_extend(pk, L, s));
             rd.skip(tot);
-            zz++;
         }
         if (rd.rel > end_rel + 7) err |= BJ_ERR_OVERRUN;
         if (err == 0) {

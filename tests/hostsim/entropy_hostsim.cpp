@@ -62,6 +62,7 @@ static ScanCtx make_ctx(const SimScan& s) {
         c.ac_tab[i] = s.ac_tab[i];
         c.slot_comp[i] = s.slot_comp[i];
     }
+    ctx_finish(c);
     c.nslots = s.nslots;
     c.ss = s.ss;
     c.se = s.se;
