@@ -61,6 +61,126 @@ def make_files(n_distinct: int, seed0: int = 0):
     return [encode_one(s) for s in range(seed0, seed0 + n_distinct)]
 
 
+def synth_jpeg(w: int, h: int, seed: int, mode: str = "RGB", **save_kw) -> bytes:
+    """One Pillow-encoded synthetic image of the SURVEY 8(d) generator (quality 75 unless overridden)."""
+    from PIL import Image
+    img = synth_image(seed, w, h)
+    im = Image.fromarray(img[..., 1] if mode == "L" else img)
+    b = io.BytesIO()
+    save_kw.setdefault("quality", 75)
+    im.save(b, "JPEG", **save_kw)
+    return b.getvalue()
+
+
+def _scan_bytes(data: bytes) -> int:
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    return sum(sc.data_end - sc.data_start for sc in parse_jpeg(data).scans)
+
+
+def bench_configs(dev) -> dict:
+    """The other shapes BASELINE.json names (configs 0, 1, 2, 4), each through the product's own entry points:
+    latency of one decode and MP/s / bitstream GB/s, measured with wall clock around synchronised calls."""
+    import tempfile
+    import torch
+    from pyjpegdecoder_b200 import JpegDecoder
+    from pyjpegdecoder_b200.pipeline import decode_batch_on_device
+    out = {}
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(dev)
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+
+    def entry(datas, sec, what, **extra):
+        from pyjpegdecoder_b200.parser import parse_jpeg
+        mp = sum(p.width * p.height for p in map(parse_jpeg, datas)) / 1e6
+        sb = sum(_scan_bytes(d) for d in datas)
+        e = {"images": len(datas), "megapixels": mp, "ms": sec * 1e3, "mp_s": mp / sec, "bitstream_gbs": sb / sec / 1e9, "what": what}
+        e.update(extra)
+        return e
+
+    # C1: the reference's own CPU-runnable case, through the literal drop-in call JpegDecoder(path).image_array
+    c1 = synth_jpeg(512, 512, 0, subsampling=2)
+    with tempfile.TemporaryDirectory() as td:
+        path = Path(td) / "c1.jpg"
+        path.write_bytes(c1)
+        sec = timed(lambda: JpegDecoder(path, device=dev).image_array, reps=20, warm=3)
+    out["c1_single_512"] = entry([c1], sec, "JpegDecoder(Path).image_array: file read + parse + H2D + kernels + D2H of the pixels "
+                                 "(jpeg_decoder.py:29-110), median of 20")
+    # C2: 3840x2160 with restart intervals (one MCU row / 16 MCUs per interval), one image per decode
+    for key, kw in (("c2_4k_dri_rows1", dict(restart_marker_rows=1)), ("c2_4k_dri_blocks16", dict(restart_marker_blocks=16))):
+        d = synth_jpeg(3840, 2160, 1, subsampling=2, **kw)
+        sec = timed(lambda: decode_batch_on_device([d], device=dev), reps=10)
+        out[key] = entry([d], sec, "decode_batch_on_device([bytes]): parse + H2D + kernels + status, pixels stay on the device, median of 10")
+    # C3: progressive, 10 scans with successive approximation: the reference's own example file (DRI) and a synthetic one (no DRI)
+    base = ROOT / "tests" / "golden" / "base_image.jpg"
+    c3 = [("c3_progressive_reference_file", base.read_bytes())] if base.exists() else []
+    c3.append(("c3_progressive_synthetic_no_dri", synth_jpeg(4160, 2340, 7, subsampling=2, progressive=True)))
+    for key, d in c3:
+        sec = timed(lambda: decode_batch_on_device([d], device=dev), reps=5)
+        out[key] = entry([d], sec, "decode_batch_on_device([bytes]), one 4160x2340 progressive image, median of 5")
+    # C5: mixed-subsampling 8192x8192 batch, baseline + progressive (grey, 4:2:2, 4:4:4), one batch of 6
+    c5 = []
+    for prog in (False, True):
+        c5.append(synth_jpeg(8192, 8192, 11, mode="L", progressive=prog))
+        c5.append(synth_jpeg(8192, 8192, 12, subsampling=1, progressive=prog))
+        c5.append(synth_jpeg(8192, 8192, 13, subsampling=0, progressive=prog))
+    sec = timed(lambda: decode_batch_on_device(c5[:3], device=dev), reps=3, warm=1)
+    out["c5_mixed_8192_baseline"] = entry(c5[:3], sec, "decode_batch_on_device: grey + 4:2:2 + 4:4:4 baseline 8192x8192 in one batch, median of 3")
+    sec = timed(lambda: decode_batch_on_device(c5, device=dev), reps=3, warm=1)
+    out["c5_mixed_8192_baseline_and_progressive"] = entry(c5, sec, "the same three plus their progressive encodings (6 images), median of 3")
+    torch.cuda.empty_cache()
+    return out
+
+
+def python_reference_c1() -> dict:
+    """The UNMODIFIED reference (baseline/_ref/jpeg_decoder.py, copied there by __graft_entry__.build()) on the C1 file,
+    one host core.  Its GUI call is patched out, its progress prints are discarded."""
+    ref_dir = ROOT / "baseline" / "_ref"
+    if not (ref_dir / "jpeg_decoder.py").exists():
+        return {"unavailable": "baseline/_ref/jpeg_decoder.py is missing (run __graft_entry__.build() where /root/reference exists)"}
+    import contextlib
+    import tempfile
+    sys.path.insert(0, str(ref_dir))
+    try:
+        import jpeg_decoder as ref
+        ref.JpegDecoder.show = lambda self: None
+        data = synth_jpeg(512, 512, 0, subsampling=2)
+        with tempfile.TemporaryDirectory() as td:
+            path = Path(td) / "c1.jpg"
+            path.write_bytes(data)
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                d = ref.JpegDecoder(path)
+            dt = time.perf_counter() - t0
+        assert d.image_array.shape == (512, 512, 3)
+        return {"value": 512 * 512 / 1e6 / dt, "unit": "MP/s", "cores": 1, "kind": "reference", "seconds": dt,
+                "sample": "one 512x512 4:2:0 q75 file (BASELINE.json configs[0]) through the unmodified jpeg_decoder.JpegDecoder(Path)"}
+    except Exception as e:  # noqa: BLE001 -- the baseline must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    finally:
+        sys.path.remove(str(ref_dir))
+
+
+def measured_traffic() -> dict:
+    """DRAM bytes (read + write) per image and kernel from the latest `ncu --set full` capture of this build, written by
+    tools/ncu_traffic.py into profiles/; absent -> traffic is reported as null."""
+    p = ROOT / "profiles" / "r2_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            pass
+    return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -170,6 +290,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=8, help="sub-batches per GPU, one CUDA stream each")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic images (cycled to --images)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="images decoded by the 1-core CPU baseline")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-shape `configs` measurements and the Python-reference timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -316,21 +437,20 @@ def main():
         else:
             stages[k] = {"ms": ms, "share_of_step": ms / sum(stage_ms.values())}
     dom = max((k for k in stages if "gbs" in stages[k]), key=lambda k: stages[k]["ms"])
-    # dram__bytes_read.sum + dram__bytes_write.sum per image from the ncu --set full captures under profiles/
-    # (r1g, 64 images per launch): measured DRAM traffic, scaled to the images one launch of this run covers
-    ncu_traffic_per_image = {"pixels": (401.184512e6 + 354.579968e6) / 64, "write": (31.864320e6 + 348.049152e6) / 64,
-                             "spec": 24.421376e6 / 64, "fix": (19.857408e6 + 3.593472e6) / 64,
-                             "unstuff": (24.596224e6 + 24.657920e6) / 64}
+    # dram__bytes_read.sum + dram__bytes_write.sum per image, from the ncu --set full capture of THIS build that
+    # tools/ncu_traffic.py summarised into profiles/r2_traffic.json (null when that file is absent)
+    traffic = measured_traffic()
+    ncu_traffic_per_image = traffic.get("bytes_per_image", {})
     img_per_launch = n_img / n_chunks
     names = {"unstuff": "unstuff_count/scan_tiles/unstuff_scatter", "spec": "spec_kernel", "fix": "fix_local_kernel + chain_kernel",
-             "write": "write_kernel", "pixels": "bj_pixels_fast_kernel<2,2,3> (fused dezigzag+dequant+IDCT+upsample+colour)"}
+             "write": "write_kernel", "pixels": "bj_pixels_420_kernel (fused dezigzag+dequant+IDCT+upsample+colour)"}
 
     def roof(k):
         st = stages.get(k, {})
         tr = ncu_traffic_per_image.get(k)
         return {"kernel": names[k], "bound": "hbm", "achieved": st.get("gbs"), "peak": peak, "unit": "GB/s",
                 "frac": st.get("frac_of_peak"), "traffic": (tr * img_per_launch) if tr else None,
-                "traffic_source": "ncu --set full capture profiles/r1g_full_summary.csv (64 images), scaled per image",
+                "traffic_source": traffic.get("source") if tr else None,
                 "peak_source": peak_src, "launches_per_step": n_chunks,
                 "algorithmic_bytes_per_launch": alg[k] / n_chunks, "ms_per_launch": st.get("ms", 0.0) / n_chunks,
                 "share_of_step": st.get("share_of_step")}
@@ -370,6 +490,9 @@ def main():
         cpu = {"value": len(sample) * W * H / 1e6 / dt, "unit": "MP/s", "cores": 1, "kind": "port",
                "sample": f"{len(sample)} of the same 1080p files, oracle C port (oracle/jpeg_oracle.c), 1 thread, {dt:.1f} s"}
 
+    configs = bench_configs(dev) if (world == 1 and not args.no_configs) else None
+    cpu_python = python_reference_c1() if (world == 1 and not args.no_configs) else None
+
     line = {
         "metric": "decoded MP/s (1080p 4:2:0 batch)", "value": mp_per_step * world / (ms_dev * 1e-3), "unit": "MP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
@@ -388,7 +511,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline, "roofline_pixels": roofline_pixels, "stages": stages,
         "bitstream_gbs": {k: scan_bytes / (stage_ms[k] * 1e-3) / 1e9 for k in ("unstuff", "spec", "write") if k in stage_ms},
-        "cpu_baseline": cpu, "public_api_e2e": api,
+        "cpu_baseline": cpu, "cpu_baseline_python": cpu_python, "public_api_e2e": api, "configs": configs,
         "device_bytes": device_bytes, "gen_seconds": t_gen,
     }
     print(json.dumps(line), flush=True)
