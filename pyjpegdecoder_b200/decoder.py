@@ -136,9 +136,29 @@ class JpegDecoder:
         return self._batch.coefficient_grids(self._index)
 
 
-def decode_batch(files: Sequence[Union[str, Path, bytes]], device: Optional[Union[str, torch.device]] = None) -> List[JpegDecoder]:
-    """Decode many files in one device pipeline (one launch sequence for the whole batch) and return
-    one JpegDecoder-like object per file."""
+# files per sub-batch when decode_batch() pipelines a large batch (see loader.decode_stream)
+BATCH_CHUNK = 512
+
+
+def decode_batch(files: Sequence[Union[str, Path, bytes]], device: Optional[Union[str, torch.device]] = None,
+                 chunk: Optional[int] = None) -> List[JpegDecoder]:
+    """Decode many files and return one JpegDecoder-like object per file (pixels stay on the device until
+    `image_array` is read).  Small batches run as ONE device pipeline (one launch sequence for all files); batches
+    larger than 1.5 x `chunk` files are cut into sub-batches of `chunk` files that flow through the streaming front
+    end (loader.decode_stream): a worker thread gathers, uploads and plans sub-batch k+1 while the GPU decodes
+    sub-batch k, so the host work hides behind the device time."""
+    files = list(files)
+    if not files:
+        return []
+    chunk = BATCH_CHUNK if chunk is None else int(chunk)
+    if chunk < 1:
+        raise ValueError("chunk must be positive")
+    if len(files) > chunk + chunk // 2:
+        from .loader import decode_stream
+        out: List[JpegDecoder] = []
+        for part in decode_stream(files, chunk=chunk, device=device):
+            out.extend(part)
+        return out
     datas = [_read(f) for f in files]
     batch = decode_batch_on_device(datas, device=device)
     return [JpegDecoder(f, _batch=batch, _index=i) for i, f in enumerate(files)]

@@ -32,63 +32,92 @@ def _chunks(files: Iterable[Source], n: int) -> Iterator[List[Source]]:
         yield buf
 
 
-_N_SLOTS = 3
+_N_SLOTS = 4
+_N_STREAMS = 3
 _WORKERS = 1
 
 
+_STREAM_POOL = {}
+
+
+def _device_streams(dev: torch.device):
+    """The copy stream and the compute streams of the streaming front end, created once per device: PyTorch's caching
+    allocator keeps freed blocks per stream, so fresh streams on every call would never get to reuse the tens of GB a
+    large batch allocates (and sooner or later trigger a full cache flush in the middle of a decode)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _STREAM_POOL:
+        with torch.cuda.device(dev):
+            _STREAM_POOL[key] = (torch.cuda.Stream(dev), [torch.cuda.Stream(dev) for _ in range(_N_STREAMS)])
+    return _STREAM_POOL[key]
+
+
 class _Uploader:
-    """Pinned staging slots + a copy stream: the upload of chunk k+1 runs while chunk k is being decoded."""
+    """Pinned staging buffers + a copy stream: the upload of chunk k+1 runs while chunk k is being decoded.  The
+    buffers come from the process-wide pool of pipeline.pack_files (pinning memory costs ~0.5 ms per MB, so they
+    are reused from call to call) and go back to it once the copy that reads them has completed."""
 
     def __init__(self, device):
         self.dev = require_cuda(device)
-        with torch.cuda.device(self.dev):
-            self.stream = torch.cuda.Stream(self.dev)
-        self.done: List[Optional[torch.cuda.Event]] = [None] * _N_SLOTS
+        self.stream = _device_streams(self.dev)[0]
+        self.inflight: List = []          # (copy-done event, pinned file buffer, pinned descriptor buffer)
+        self.desc_free: List[torch.Tensor] = []
+
+    def _reclaim(self, block: bool) -> None:
+        from .pipeline import release_pinned
+        while self.inflight and (block and len(self.inflight) >= _N_SLOTS or self.inflight[0][0].query()):
+            ev, buf, dbuf = self.inflight.pop(0)
+            ev.synchronize()
+            release_pinned(buf)
+            self.desc_free.append(dbuf)
 
     def prepare(self, files: Sequence[Source], k: int, read_threads: int = 8):
-        """Host side of chunk k: read, gather into a pinned slot, start the H2D copy, plan."""
+        """Host side of chunk k: read, gather into a pinned buffer, start the H2D copy, plan, upload the descriptors."""
+        from .pipeline import upload_descriptors
         if any(not isinstance(f, (bytes, bytearray, memoryview)) for f in files) and len(files) > 1:
             with ThreadPoolExecutor(min(read_threads, len(files))) as ex:
                 datas = list(ex.map(_read, files))
         else:
             datas = [_read(f) for f in files]
-        slot = k % _N_SLOTS
-        if self.done[slot] is not None:
-            self.done[slot].synchronize()          # the copy that last read this pinned slot has finished
-        packed = pack_files(datas, pin=True, reuse_slot=("loader", id(self), slot), walk=len(datas) >= FAST_PLAN_MIN_FILES)
+        self._reclaim(block=True)
+        packed = pack_files(datas, pin=True, reuse_slot="checkout", walk=len(datas) >= FAST_PLAN_MIN_FILES)
         raw_host, offsets = packed
         with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
             raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=self.dev)
             raw_dev.copy_(raw_host, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self.done[slot] = ev
         if len(datas) >= FAST_PLAN_MIN_FILES:
             from .fastplan import plan_batch
             plan = plan_batch(raw_host, offsets, [len(d) for d in datas], walked=getattr(raw_host, "_bj_walk", None))
         else:
             plan = BatchPlan([parse_jpeg(d) for d in datas], offsets, raw_host.numel())
-        return list(files), packed, plan, raw_dev, ev
-
+        dbuf = self.desc_free.pop() if self.desc_free else None
+        desc_blob, layout, dbuf = upload_descriptors(plan, self.dev, self.stream, dbuf)
+        ev = torch.cuda.Event()
+        with torch.cuda.device(self.dev):
+            ev.record(self.stream)
+        self.inflight.append((ev, raw_host, dbuf))
+        return list(files), packed, plan, raw_dev, ev, (desc_blob, layout)
 
     def close(self) -> None:
-        from .pipeline import _PINNED_POOL
-        for slot in range(_N_SLOTS):
-            if self.done[slot] is not None:
-                self.done[slot].synchronize()
-            _PINNED_POOL.pop(("loader", id(self), slot), None)
+        from .pipeline import release_pinned
+        for ev, buf, _ in self.inflight:
+            ev.synchronize()
+            release_pinned(buf)
+        self.inflight = []
 
 
 def _check(batch) -> None:
-    raise_for_errors(batch.stats["_pipe"].err.cpu().numpy())
+    pipe = batch.stats["_pipe"]
+    pipe.stream.synchronize()                 # the chunk ran on its own stream: everything it produced is complete now
+    raise_for_errors(pipe.err.cpu().numpy())
 
 
 def decode_stream(files: Iterable[Source], chunk: int = 512, device: Optional[Union[str, torch.device]] = None
                   ) -> Iterator[List[JpegDecoder]]:
     """Decode an arbitrarily long sequence of files `chunk` at a time; yields one list of JpegDecoder objects
     per chunk, in order.  Errors of a file (NotJpeg, CorruptedJpeg, ...) are raised when its chunk is reached.
-    Three things overlap: the worker thread prepares and uploads chunk k+1, the GPU decodes chunk k (its kernels
-    are enqueued before chunk k-1 is checked), and the caller consumes chunk k-1."""
+    Three things overlap: the worker thread prepares and uploads the chunks ahead, the GPU decodes up to three chunks
+    on alternating streams (a chunk is checked only when two later ones have been enqueued), and the caller consumes
+    the oldest finished chunk."""
     if chunk < 1:
         raise ValueError("chunk must be positive")
     up = _Uploader(device)
@@ -101,6 +130,10 @@ def decode_stream(files: Iterable[Source], chunk: int = 512, device: Optional[Un
 
 
 def _stream(up, it, depth, device):
+    # consecutive chunks run on alternating streams: the latency-bound tail of chunk k (a few long-running CTAs, the
+    # one-CTA-per-scan prefix kernel) overlaps the start of chunk k+1 instead of leaving the GPU half empty
+    streams = _device_streams(up.dev)[1]
+    n_done = 0
     with ThreadPoolExecutor(_WORKERS) as worker:
         queue = []
         k = 0
@@ -115,17 +148,22 @@ def _stream(up, it, depth, device):
                 k += 1
 
         refill()
-        prev = None
+        pending = []          # enqueued, not yet checked: up to _N_STREAMS - 1 chunks run ahead of the one being consumed
         while queue:
-            chunk_files, packed, plan, raw_dev, ev = queue.pop(0).result()
+            chunk_files, packed, plan, raw_dev, ev, desc = queue.pop(0).result()
             refill()
-            raw_dev.record_stream(torch.cuda.current_stream(up.dev))
+            st = streams[n_done % _N_STREAMS]
+            n_done += 1
+            raw_dev.record_stream(st)
+            desc[0].record_stream(st)
             batch = decode_batch_on_device(None, device=device, packed=packed, plan=plan, check=False,
-                                           raw_dev=raw_dev, raw_ready=ev)
-            if prev is not None:
-                _check(prev[0])
-                yield [JpegDecoder(f, _batch=prev[0], _index=i) for i, f in enumerate(prev[1])]
-            prev = (batch, chunk_files)
-        if prev is not None:
-            _check(prev[0])
-            yield [JpegDecoder(f, _batch=prev[0], _index=i) for i, f in enumerate(prev[1])]
+                                           raw_dev=raw_dev, raw_ready=ev, desc=desc, stream=st)
+            pending.append((batch, chunk_files))
+            if len(pending) >= _N_STREAMS:
+                b, fl = pending.pop(0)
+                _check(b)
+                yield [JpegDecoder(f, _batch=b, _index=i) for i, f in enumerate(fl)]
+        while pending:
+            b, fl = pending.pop(0)
+            _check(b)
+            yield [JpegDecoder(f, _batch=b, _index=i) for i, f in enumerate(fl)]

@@ -240,7 +240,7 @@ def release_pinned(buf: torch.Tensor) -> None:
         return
     with _PINNED_LOCK:
         _PINNED_FREE.append(pool)
-        if len(_PINNED_FREE) > 4:                  # keep the largest few
+        if len(_PINNED_FREE) > 8:                  # keep the largest few
             _PINNED_FREE.sort(key=lambda t: t.numel())
             _PINNED_FREE.pop(0)
 
@@ -303,6 +303,43 @@ def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot=None, walk: 
         for d, off in zip(datas, offsets):
             view[off:off + len(d)] = np.frombuffer(d, dtype=np.uint8)
     return buf, offsets
+
+
+_DESC_FIELDS = ("scans", "tile_scan", "lut", "images", "qtabs")
+
+
+def descriptor_blob(plan) -> Tuple[np.ndarray, Dict[str, Tuple[int, int]]]:
+    """All small per-batch arrays the kernels read (scan records, tile table, Huffman LUTs, image records, quantisation
+    tables) as ONE byte blob with 256-byte aligned sections: one asynchronous copy from pinned memory instead of five
+    blocking ones from pageable memory (each of which would wait for everything queued on the stream)."""
+    parts = {"scans": plan.scans, "tile_scan": plan.tile_scan, "lut": plan.lut, "images": plan.geom.images,
+             "qtabs": plan.geom.qtabs}
+    layout: Dict[str, Tuple[int, int]] = {}
+    total = 0
+    for k in _DESC_FIELDS:
+        a = np.ascontiguousarray(parts[k])
+        total = (total + 255) & ~255
+        layout[k] = (total, a.nbytes)
+        total += a.nbytes
+    blob = np.zeros(max(total, 16), dtype=np.uint8)
+    for k in _DESC_FIELDS:
+        a = np.ascontiguousarray(parts[k])
+        o, n = layout[k]
+        blob[o:o + n] = a.view(np.uint8).reshape(-1)
+    return blob, layout
+
+
+def upload_descriptors(plan, device, stream: torch.cuda.Stream, pinned: Optional[torch.Tensor] = None):
+    """Copy descriptor_blob(plan) to the device on `stream` (non-blocking, from pinned memory).  Returns
+    (device blob, layout, pinned staging buffer -- keep it alive until the copy has completed)."""
+    blob, layout = descriptor_blob(plan)
+    if pinned is None or pinned.numel() < blob.size:
+        pinned = torch.empty(max(blob.size, 1 << 16) * 2, dtype=torch.uint8, pin_memory=True)
+    pinned[:blob.size].numpy()[:] = blob
+    with torch.cuda.device(device), torch.cuda.stream(stream):
+        dev_blob = torch.empty(blob.size, dtype=torch.uint8, device=device)
+        dev_blob.copy_(pinned[:blob.size], non_blocking=True)
+    return dev_blob, layout, pinned
 
 
 class _LazyViews:
@@ -380,9 +417,10 @@ class DevicePipeline:
     STAGES = ("unstuff", "plan", "spec", "fix", "write", "other_scans", "pixels")
 
     def __init__(self, plan: BatchPlan, device=None, stream: Optional[torch.cuda.Stream] = None,
-                 raw: Optional[torch.Tensor] = None):
+                 raw: Optional[torch.Tensor] = None, desc: Optional[Tuple[torch.Tensor, Dict[str, Tuple[int, int]]]] = None):
         """raw: device copy of the packed file bytes, if the caller has already started it (see
-        decode_batch_on_device: the H2D copy runs while the host is still planning)."""
+        decode_batch_on_device: the H2D copy runs while the host is still planning).
+        desc: (device blob, layout) from upload_descriptors(), if the caller uploaded the descriptors already."""
         self.plan = plan
         self.dev = require_cuda(device)
         self.L = _bind()
@@ -391,10 +429,19 @@ class DevicePipeline:
         with torch.cuda.device(dev):
             self.stream = stream if stream is not None else torch.cuda.current_stream(dev)
             with torch.cuda.stream(self.stream):
-                self.scans = to_device(plan.scans, dev)
-                self.tile_scan = to_device(plan.tile_scan, dev)
-                self.lut = torch.from_numpy(plan.lut.view(np.int32)).to(dev)
-                self.dg = DeviceGeometry(g, dev)
+                if desc is None:
+                    desc_blob, layout, self._desc_pinned = upload_descriptors(plan, dev, self.stream)
+                else:
+                    desc_blob, layout = desc
+                self._desc = desc_blob
+
+                def sect(k):
+                    o, n = layout[k]
+                    return desc_blob[o:o + n]
+                self.scans = sect("scans")
+                self.tile_scan = sect("tile_scan")
+                self.lut = sect("lut")
+                self.dg = DeviceGeometry(g, dev, images=sect("images"), qtabs=sect("qtabs"))
                 self.raw = raw if raw is not None else torch.empty(plan.raw_bytes, dtype=torch.uint8, device=dev)
                 if self.raw.numel() != plan.raw_bytes or not self.raw.is_cuda:
                     raise ValueError("raw: wrong size or not a device tensor")
@@ -508,7 +555,8 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
                            packed: Optional[Tuple[torch.Tensor, List[int]]] = None, check: bool = True,
                            stream: Optional[torch.cuda.Stream] = None, upto_wave: Optional[int] = None,
                            plan: Optional[BatchPlan] = None, out_kind: int = _native.OUT_RGB,
-                           raw_dev: Optional[torch.Tensor] = None, raw_ready: Optional[torch.cuda.Event] = None) -> DecodedBatch:
+                           raw_dev: Optional[torch.Tensor] = None, raw_ready: Optional[torch.cuda.Event] = None,
+                           desc=None) -> DecodedBatch:
     """Decode a batch of JPEG file images on one GPU.  Returns device tensors; with check=True the
     per-image error words are read back (one synchronisation) and turned into exceptions.
     upto_wave=k stops the entropy stage after the first k scan groups (tests: per-scan parity)."""
@@ -536,7 +584,7 @@ def decode_batch_on_device(datas: Optional[Sequence[bytes]], device=None, parsed
             if parsed is None:
                 parsed = [parse_jpeg(d) for d in datas]
             plan = BatchPlan(parsed, offsets, raw_host.numel(), serial_scans=upto_wave is not None)
-    pipe = DevicePipeline(plan, device, stream, raw=raw_dev)
+    pipe = DevicePipeline(plan, device, stream, raw=raw_dev, desc=desc)
     pipe.launch(out_kind=out_kind, upto_group=upto_wave)
     res = pipe.result()
     if check:

@@ -39,11 +39,13 @@ def device_idct_table(device) -> torch.Tensor:
 class DeviceGeometry:
     """BatchGeometry uploaded to one device."""
 
-    def __init__(self, geom: BatchGeometry, device):
+    def __init__(self, geom: BatchGeometry, device, images: Optional[torch.Tensor] = None,
+                 qtabs: Optional[torch.Tensor] = None):
+        """images / qtabs: device copies that already exist (pipeline.upload_descriptors), else uploaded here."""
         self.geom = geom
         self.device = device
-        self.images = to_device(geom.images, device)
-        self.qtabs = to_device(geom.qtabs, device)
+        self.images = images if images is not None else to_device(geom.images, device)
+        self.qtabs = qtabs if qtabs is not None else to_device(geom.qtabs, device)
         self.table = device_idct_table(device)
 
 

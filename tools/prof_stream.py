@@ -27,13 +27,13 @@ for rep in range(3):
         prev = None
         while queue:
             t0 = time.perf_counter()
-            chunk_files, packed, plan, raw_dev, ev = queue.pop(0).result()
+            chunk_files, packed, plan, raw_dev, ev, desc = queue.pop(0).result()
             t1 = time.perf_counter(); T["wait"] += t1 - t0
             refill()
             raw_dev.record_stream(torch.cuda.current_stream(up.dev))
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
             a.record()
-            batch = decode_batch_on_device(None, device="cuda:0", packed=packed, plan=plan, check=False, raw_dev=raw_dev, raw_ready=ev)
+            batch = decode_batch_on_device(None, device="cuda:0", packed=packed, plan=plan, check=False, raw_dev=raw_dev, raw_ready=ev, desc=desc)
             b.record(); evs.append((a, b))
             t2 = time.perf_counter(); T["enq"] += t2 - t1
             if prev is not None:
