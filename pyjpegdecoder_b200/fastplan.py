@@ -61,7 +61,8 @@ def walk_batch(raw: np.ndarray, offsets: np.ndarray, sizes: np.ndarray, threads:
     counts = np.empty(n, dtype=np.int32)
     hashes = np.empty((n, 2), dtype=np.uint64)
     if threads is None:
-        threads = min(16, os.cpu_count() or 1)
+        from .pipeline import host_threads
+        threads = host_threads()
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
     _lib().bj_host_walk_batch_keys(raw.ctypes.data, offsets.ctypes.data, sizes.ctypes.data, n, entries.ctypes.data,

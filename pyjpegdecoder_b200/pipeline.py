@@ -207,6 +207,16 @@ class BatchPlan:
                              if g.mode in (0, 1, 3)) if any(g.mode in (0, 1, 3) for g in self.groups) else 1
 
 
+def host_threads() -> int:
+    """Host threads of the C gather / marker-walk helpers: BJ_HOST_THREADS, else the cores of the box divided among
+    the ranks of a one-process-per-GPU launch (LOCAL_WORLD_SIZE), at most 16."""
+    env = os.environ.get("BJ_HOST_THREADS")
+    if env:
+        return max(1, int(env))
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(16, (os.cpu_count() or 1) // ranks))
+
+
 def covers_all_components(p: ParsedJpeg) -> bool:
     """True if the scans of a baseline image write every coefficient block (the write kernel stores whole blocks,
     so the coefficient buffer then needs no memset).  A truncated non-interleaved file leaves components unscanned:
@@ -287,7 +297,7 @@ def pack_files(datas: Sequence[bytes], pin: bool = True, reuse_slot=None, walk: 
         ptrs = (ctypes.c_char_p * n)(*datas)
         sizes = np.fromiter((len(d) for d in datas), dtype=np.uint64, count=n)
         offs = np.asarray(offsets, dtype=np.uint64)
-        threads = min(16, os.cpu_count() or 1)
+        threads = host_threads()
         if walk:
             from .fastplan import ENTRY_DTYPE, MAX_ENTRIES
             entries = np.empty((n, MAX_ENTRIES), dtype=ENTRY_DTYPE)
