@@ -5,7 +5,8 @@
 The reference cannot travel to the GPU box, so its outputs are committed here as small
 fixtures together with this script (the only file that imports the reference).
 
-Usage:  python tests/golden/make_golden.py [--big]     (needs /root/reference, Pillow, scipy)
+Usage:  python tests/golden/make_golden.py [--big | --writer]     (needs /root/reference, Pillow, scipy)
+        --writer: only the cases written by tests/jpeg_writer.py (sampling layouts Pillow cannot encode, int16 wrap)
 
 What is recorded per case (tests/golden/cases/<name>.jpg + <name>.npz):
   rgb      uint8  (W,H,3) or (W,H)  -- JpegDecoder.image_array            (jpeg_decoder.py:1373-1386)
@@ -306,6 +307,41 @@ def big_fixture(meta):
     print("base_image", entry["rgb_sha256"], flush=True)
 
 
+def writer_cases():
+    """Files Pillow cannot encode, written by tests/jpeg_writer.py: 4:4:0, layouts whose chroma components have their
+    own sampling factors (the generic pixel kernel), and quantised coefficients whose dequantisation product wraps
+    the reference's int16 arithmetic (jpeg_decoder.py:869)."""
+    sys.path.insert(0, str(HERE.parent))
+    import jpeg_writer as jw
+    qt = jw.std_qtables(75)
+    out = []
+
+    def from_image(name, w, h, seed, sampling, ri=0):
+        img = synth(w, h, seed)
+        comps = jw.image_to_components(img, sampling, qt)
+        out.append((name, jw.write_baseline(w, h, comps, qt, restart_interval=ri)))
+
+    from_image("w440_40x48", 40, 48, 401, [(1, 2), (1, 1), (1, 1)])
+    from_image("w440_33x41_dri3", 33, 41, 402, [(1, 2), (1, 1), (1, 1)], ri=3)
+    from_image("w440_96x80", 96, 80, 403, [(1, 2), (1, 1), (1, 1)])
+    from_image("wgen_y22_cb21_cr11_48x48", 48, 48, 404, [(2, 2), (2, 1), (1, 1)])
+    from_image("wgen_y22_cb12_cr11_50x37", 50, 37, 405, [(2, 2), (1, 2), (1, 1)])
+    from_image("wgen_y21_cb11_cr21_64x24", 64, 24, 406, [(2, 1), (1, 1), (2, 1)])
+    from_image("wgen_y22_cb22_cr11_32x32", 32, 32, 407, [(2, 2), (2, 2), (1, 1)])
+    # int16 wrap of coefficient * Q: quantisation tables full of 255, DC and a few AC coefficients beyond 128
+    rng = np.random.default_rng(408)
+    q255 = {0: [255] * 64, 1: [255] * 64}
+    comps = []
+    for i in range(3):
+        blocks = np.zeros((2, 2, 64), np.int32)
+        blocks[..., 0] = rng.integers(-4, 5, (2, 2)) * 40 + np.array([[200, -150], [135, 129]])   # |DC * 255| > 32767
+        blocks[..., 1] = rng.integers(-140, 141, (2, 2))
+        blocks[..., 5] = rng.integers(-3, 4, (2, 2))
+        comps.append({"h": 1, "v": 1, "tq": 0 if i == 0 else 1, "blocks": blocks})
+    out.append(("wwrap_16x16_ss0", jw.write_baseline(16, 16, comps, q255)))
+    return out
+
+
 def main():
     CASES.mkdir(parents=True, exist_ok=True)
     meta_path = HERE / "golden.json"
@@ -315,6 +351,9 @@ def main():
                         "pillow": __import__("PIL").__version__}
     if "--big" in sys.argv:
         big_fixture(meta)
+    elif "--writer" in sys.argv:
+        for name, data in writer_cases():
+            record_case(name, data, meta["cases"])
     else:
         for (name, w, h, seed, ch, kw, sat) in small_cases():
             img = synth(w, h, seed, ch, sat)

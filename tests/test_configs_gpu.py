@@ -72,6 +72,33 @@ def test_config5_progressive_mixed_subsampling(kind):
     _check([_encode(2048, 2048, 6, progressive=True, **kw)])
 
 
+@pytest.mark.parametrize("kind", ["gray", "422", "444"])
+def test_config5_8192x8192_progressive(kind):
+    """BASELINE.json configs[4] at its full size in progressive mode (10 scans / 6 for grey, no restart markers)."""
+    kw = {"gray": dict(gray=True), "422": dict(subsampling=1), "444": dict(subsampling=0)}[kind]
+    _check([_encode(8192, 8192, 15, progressive=True, **kw)])
+
+
+@pytest.mark.parametrize("name,layout", [("w440_96x80", 3), ("w440_33x41_dri3", 3), ("wgen_y22_cb21_cr11_48x48", 0),
+                                         ("wgen_y22_cb12_cr11_50x37", 0), ("wgen_y21_cb11_cr21_64x24", 0),
+                                         ("wgen_y22_cb22_cr11_32x32", 0), ("wwrap_16x16_ss0", 4)])
+def test_layouts_pillow_cannot_encode(name, layout):
+    """4:4:0 (its own kernel instance), chroma components with their own sampling factors (the generic kernel) and a
+    dequantisation product that wraps int16 (:869): files from tests/jpeg_writer.py, decoded ALONE so that the kernel
+    under test is the only one launched, against the fixtures the unmodified reference produced."""
+    from conftest import GOLDEN
+    from pyjpegdecoder_b200 import JpegDecoder
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    from pyjpegdecoder_b200.plan import layout_of
+    data = (GOLDEN / "cases" / f"{name}.jpg").read_bytes()
+    z = np.load(GOLDEN / "cases" / f"{name}.npz")
+    assert layout_of(parse_jpeg(data)) == layout
+    d = JpegDecoder(data, device="cuda:0")
+    assert np.array_equal(d.image_array, z["rgb"])
+    for c, plane in enumerate(d.coefficient_planes()):
+        assert np.array_equal(plane, z[f"coef{c}"])
+
+
 def test_config5_mixed_batch_one_launch_sequence():
     """grey + 4:2:2 + 4:4:4 + 4:2:0, baseline and progressive, odd sizes, in ONE batch."""
     datas = [_encode(1000, 700, 7, gray=True), _encode(1023, 769, 8, subsampling=1),
