@@ -168,3 +168,50 @@ def test_unscanned_components_force_a_zeroed_coefficient_buffer():
     assert covers_all_components(p)
     p.scans[0].comps = (0,)
     assert not covers_all_components(p)
+
+
+def test_header_fuzz_only_jpeg_errors_and_in_bounds_plans():
+    """Random byte flips in the marker segments (SOF, DHT, DQT, DRI, SOS lengths, ...): the host side either builds a
+    plan whose scan byte ranges lie inside the packed buffer, or raises a JpegError -- never another exception type,
+    never a wrapped / negative length (what the device kernels would then index with)."""
+    import numpy as np
+    from pathlib import Path
+    from pyjpegdecoder_b200.errors import JpegError
+    from pyjpegdecoder_b200.fastplan import FastPlan, _Fallback
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    from pyjpegdecoder_b200.pipeline import BatchPlan
+    cases = Path(__file__).parent / "golden" / "cases"
+    names = sorted(p.name for p in cases.glob("*.jpg"))
+    rng = np.random.default_rng(11)
+    n_ok = n_err = 0
+    for it in range(400):
+        data = bytearray((cases / names[int(rng.integers(len(names)))]).read_bytes())
+        first_scan = parse_jpeg(bytes(data)).scans[0].data_start
+        for _ in range(int(rng.integers(1, 4))):
+            pos = int(rng.integers(2, first_scan))
+            data[pos] = int(rng.integers(256)) if rng.random() < 0.5 else data[pos] ^ (1 << int(rng.integers(8)))
+        bad = bytes(data)
+        files = [bad] * 5
+        offs, total = [], 0
+        for f in files:
+            offs.append(total)
+            total += (len(f) + 15) & ~15
+        raw = np.zeros(total + 64, np.uint8)
+        for f, o in zip(files, offs):
+            raw[o:o + len(f)] = np.frombuffer(f, np.uint8)
+        plans = []
+        try:
+            plans.append(BatchPlan([parse_jpeg(bad)], [0], len(bad) + 64))
+        except JpegError:
+            n_err += 1
+        try:
+            plans.append(FastPlan(raw, offs, [len(f) for f in files]))
+        except (JpegError, _Fallback):
+            pass
+        for plan in plans:
+            n_ok += 1
+            sc = plan.scans
+            assert (sc["raw_off"].astype(np.int64) + sc["raw_len"].astype(np.int64) <= plan.raw_bytes).all()
+            assert (sc["raw_len"].astype(np.int64) < 2 ** 31).all() and (sc["n_sub_max"].astype(np.int64) < 2 ** 31).all()
+            assert plan.geom.total_blocks < 2 ** 31 and plan.geom.out_bytes < 2 ** 40
+    assert n_ok > 50 and n_err > 50
