@@ -51,7 +51,7 @@ typedef int bj_status;
 #define BJ_ERR_BAD_CODE 1u      /* no Huffman code within 16 bits   -> CorruptedJpeg (:718-719, :957-958) */
 #define BJ_ERR_OVERRUN 2u       /* entropy data ended early          -> IndexError in the reference */
 #define BJ_ERR_RST_COUNT 4u     /* fewer restart markers than the MCU count requires */
-#define BJ_ERR_SYNC 8u          /* internal: speculative decode did not converge (host retries) */
+#define BJ_ERR_SYNC 8u          /* internal: more subsequences than the host reserved slots for (planning bug) */
 #define BJ_ERR_COEF_INDEX 16u   /* coefficient index ran past 63 in a progressive scan */
 
 #define BJ_MAX_COMP 3

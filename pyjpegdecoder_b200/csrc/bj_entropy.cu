@@ -9,13 +9,13 @@
 //            every stream (exclusive scan), restart-marker count check.
 //   spec     one thread per subsequence: decode from one subsequence early (assumed block start) to
 //            obtain a speculative entry state, then the own subsequence: exit state, blocks started,
-//            DC difference sums.  The CTA's slice of the bitstream and the scan's Huffman LUTs are
-//            staged in shared memory (bank-swizzled), since every lane walks its own 128-byte region.
-//   fix      ONE launch: each CTA iterates (shared memory) until every subsequence's entry equals its
-//            predecessor's exit, then waits for the previous CTA of the scan to publish its final
-//            exit state and running totals (decoupled look-back chaining: CTAs only wait on
-//            lower-indexed CTAs), repairs if needed, computes the segmented exclusive prefix sums
-//            (block index and DC predictors per subsequence) and publishes its own totals.
+//            DC difference sums.  The scan's Huffman LUTs are staged in shared memory; the bitstream is
+//            read through L1 (every lane walks its own 512-byte region).
+//   fix      two launches.  fix_local: each CTA iterates in shared memory until every subsequence's entry
+//            equals its predecessor's exit (re-decodes compacted into a dense list per round).  chain: one
+//            CTA per scan repairs the CTA boundaries of fix_local in parallel, then computes the segmented
+//            exclusive prefix sums (block index and DC predictors per subsequence).  Nothing waits on
+//            another CTA.
 //   write    baseline: each thread owns the blocks that START in its subsequence, assembles each in a
 //            private shared-memory slot and stores it as one 128-byte line -- every block is written
 //            exactly once, no memset, no atomics.  Progressive first scans store single coefficients.
@@ -39,29 +39,8 @@ constexpr int T = BJ_ENTROPY_THREADS;
 #endif
 constexpr int TW = BJ_WRITE_THREADS;  // subsequences per CTA of write_kernel (its LUT copy is amortised over more threads)
 constexpr int S = BJ_SUBSEQ_BITS;
-constexpr int kWinWords = (T + 1) * (S / 32) + 64;  // bit window of one CTA, in 32-bit words
 constexpr int kMaxLutSmem = 12288;                  // most LUT entries ever staged in shared memory (48 KB)
 
-
-#ifndef BJ_WRITE_WINDOW
-#define BJ_WRITE_WINDOW 0  // same switch for write_kernel
-#endif
-#ifndef BJ_SPEC_WINDOW
-#define BJ_SPEC_WINDOW 0  // 1: spec_kernel stages its bit window in shared memory; 0: reads it through L1 (more CTAs per SM)
-#endif
-
-struct WinSrc {
-    const uint32_t* sw;  // shared window, swizzled
-    uint32_t w0;         // first word held in the window
-    uint32_t n;          // words in the window
-    const uint32_t* gw;  // global words
-    uint32_t gn;
-    __device__ __forceinline__ uint32_t word(uint32_t i) const {
-        uint32_t j = i - w0;
-        if (j < n) return sw[j ^ ((j >> 5) & 31u)];
-        return i < gn ? __ldg(gw + i) : 0xFFFFFFFFu;
-    }
-};
 
 struct GlobalSrc {
     const uint32_t* gw;
@@ -71,19 +50,8 @@ struct GlobalSrc {
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return __ldg(gw + min(i, gn - 1u)); }
 };
 
+// Per-CTA scan context + the scan's Huffman LUTs (the bitstream itself is read through L1)
 struct CtaShared {
-    bj_scan sc;
-    ScanCtx ctx;
-    uint32_t scan_nsub;
-    uint32_t win_w0, win_n;
-    uint32_t lut_cap;  // entries available in lut[] (dynamic shared memory)
-    uint32_t lut_in_smem;
-    uint32_t win[kWinWords];
-    uint32_t lut[1];   // lut_cap entries follow
-};
-
-// Same without the bit window (kernels that read the bitstream through L1 and spend the shared memory on occupancy)
-struct CtaSharedNoWin {
     bj_scan sc;
     ScanCtx ctx;
     uint32_t scan_nsub;
@@ -196,25 +164,6 @@ __device__ __forceinline__ SubInfo locate(const SH& sh, const bj_entropy_buffers
     return s;
 }
 
-// Stage the CTA's slice of the bitstream: words [w0, w0 + kWinWords).
-__device__ __forceinline__ void load_window(CtaShared& sh, const bj_entropy_buffers& B, uint64_t first_bit) {
-    uint32_t w0 = (uint32_t)(first_bit >> 5);
-    uint32_t gn = (uint32_t)B.words_len;
-    for (uint32_t j = threadIdx.x; j < (uint32_t)kWinWords; j += blockDim.x) {
-        uint32_t i = w0 + j;
-        sh.win[j ^ ((j >> 5) & 31u)] = i < gn ? __ldg(B.words + i) : 0xFFFFFFFFu;
-    }
-    if (threadIdx.x == 0) {
-        sh.win_w0 = w0;
-        sh.win_n = kWinWords;
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ WinSrc win_src(const CtaShared& sh, const bj_entropy_buffers& B) {
-    return WinSrc{sh.win, sh.win_w0, sh.win_n, B.words, (uint32_t)B.words_len};
-}
-
 // Decode one subsequence from entry state st: exit state + counts.  `lut` must be passed with visible
 // provenance (sh.lut -> LDS, or a global pointer).
 template <class Src>
@@ -296,28 +245,14 @@ __global__ void __launch_bounds__(256) plan_kernel(const bj_scan* __restrict__ s
 __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
                                                  uint32_t lut_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-#if BJ_SPEC_WINDOW
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
-#else
-    CtaSharedNoWin& sh = *reinterpret_cast<CtaSharedNoWin*>(smem_raw);
-#endif
     load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
     const uint32_t base = blockIdx.y * T;
     if (base >= sh.scan_nsub) return;
     const uint32_t lscan = base + threadIdx.x;
     SubInfo si = locate(sh, B, lscan);
-#if BJ_SPEC_WINDOW
-    // window starts where the first thread starts reading
-    __shared__ uint64_t first_bit;
-    if (threadIdx.x == 0) first_bit = si.l ? si.own - S : si.own;
-    __syncthreads();
-    load_window(sh, B, first_bit);
-    if (!si.valid) return;
-    WinSrc src = win_src(sh, B);
-#else
     if (!si.valid) return;
     GlobalSrc src{B.words, (uint32_t)B.words_len};
-#endif
     const int z0 = (sh.sc.mode == BJ_MODE_AC_FIRST) ? sh.sc.ss : 0;
     uint64_t st;
     if (si.l == 0) st = pack_state(si.b0, z0, 0);
@@ -594,12 +529,7 @@ struct GlobalCoefSink {  // progressive first scans: single coefficient stores
 __global__ void __launch_bounds__(TW) write_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
                                                   uint32_t lut_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-#if BJ_WRITE_WINDOW
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
-    __shared__ uint64_t first_bit;
-#else
-    CtaSharedNoWin& sh = *reinterpret_cast<CtaSharedNoWin*>(smem_raw);
-#endif
     __shared__ __align__(16) uint32_t s_blocks[TW * 32];
     load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
     const uint32_t base = blockIdx.y * TW;
@@ -607,21 +537,11 @@ __global__ void __launch_bounds__(TW) write_kernel(const bj_scan* __restrict__ s
     const int tid = threadIdx.x;
     const uint32_t lscan = base + tid;
     SubInfo si = locate(sh, B, lscan);
-#if BJ_WRITE_WINDOW
-    if (tid == 0) first_bit = si.own;
-#endif
     for (int i = tid; i < TW * 32; i += TW) s_blocks[i] = 0u;
     __syncthreads();
-#if BJ_WRITE_WINDOW
-    load_window(sh, B, first_bit);
-    if (!si.valid) return;
-    WinSrc src = win_src(sh, B);
-    typedef WinSrc SrcT;
-#else
     if (!si.valid) return;
     GlobalSrc src{B.words, (uint32_t)B.words_len};
     typedef GlobalSrc SrcT;
-#endif
     const size_t g = (size_t)sh.sc.sub0 + lscan;
     const uint64_t st = B.sub_entry[g];
     const uint4 pre = reinterpret_cast<const uint4*>(B.sub_prefix)[g];
@@ -812,7 +732,7 @@ bj_status bj_entropy_plan(const bj_scan* scans, int scan_first, int n_scans, con
 bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, int mode, uint32_t max_sub,
                             uint32_t max_streams, uint32_t max_blocks, uint32_t max_lut,
                             const bj_entropy_buffers* bufs, uint32_t* chain, int phases, void* stream) {
-    if (!scans || n_scans <= 0 || n_scans > 65535 || !bufs) return BJ_E_ARG;
+    if (!scans || n_scans <= 0 || !bufs) return BJ_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     const uint32_t lut_cap = max_lut < (uint32_t)kMaxLutSmem ? max_lut : (uint32_t)kMaxLutSmem;
@@ -826,8 +746,7 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         dim3 grid((unsigned)n_scans, (max_sub + T - 1) / T);
         if (grid.y > 65535) return BJ_E_ARG;
         if (phases & BJ_PHASE_SPEC) {
-            const size_t spec_smem = BJ_SPEC_WINDOW ? smem : sizeof(CtaSharedNoWin) + sizeof(uint32_t) * lut_cap;
-            spec_kernel<<<grid, T, spec_smem, st>>>(scans, scan_first, *bufs, lut_cap);
+            spec_kernel<<<grid, T, smem, st>>>(scans, scan_first, *bufs, lut_cap);
         }
         if (phases & BJ_PHASE_FIX) {
             fix_local_kernel<<<grid, T, 0, st>>>(scans, scan_first, *bufs);
@@ -840,21 +759,27 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
                                                                                                          bitmap_words, chain_lut);
         }
         if (phases & BJ_PHASE_WRITE) {
-            const size_t write_smem = BJ_WRITE_WINDOW ? smem : sizeof(CtaSharedNoWin) + sizeof(uint32_t) * lut_cap;
-            write_kernel<<<dim3((unsigned)n_scans, (max_sub + TW - 1) / TW), TW, write_smem, st>>>(scans, scan_first, *bufs, lut_cap);
+            write_kernel<<<dim3((unsigned)n_scans, (max_sub + TW - 1) / TW), TW, smem, st>>>(scans, scan_first, *bufs, lut_cap);
         }
     } else if (mode == BJ_MODE_DC_REFINE) {
         unsigned gx = (max_blocks + 255) / 256;
         if (gx == 0) gx = 1;
         if (gx > 4096) gx = 4096;
-        dcrefine_kernel<<<dim3(gx, (unsigned)n_scans), 256, 0, st>>>(scans, scan_first, *bufs);
+        // the scan index rides on grid.y (at most 65535): larger waves are launched in slices
+        for (int s0 = 0; s0 < n_scans; s0 += 65535) {
+            const int ns = n_scans - s0 < 65535 ? n_scans - s0 : 65535;
+            dcrefine_kernel<<<dim3(gx, (unsigned)ns), 256, 0, st>>>(scans, scan_first + s0, *bufs);
+        }
     } else if (mode == BJ_MODE_AC_REFINE) {
         if (!bufs->blk_pos || max_streams == 0 || max_blocks == 0) return BJ_E_ARG;
         e = cudaFuncSetAttribute(acrefine_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(acrefine_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
-        acrefine_parse_kernel<<<dim3(max_streams, (unsigned)n_scans), 32, smem, st>>>(scans, scan_first, *bufs, lut_cap);
-        acrefine_apply_kernel<<<dim3((max_blocks + 127) / 128, (unsigned)n_scans), 128, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+        for (int s0 = 0; s0 < n_scans; s0 += 65535) {
+            const int ns = n_scans - s0 < 65535 ? n_scans - s0 : 65535;
+            acrefine_parse_kernel<<<dim3(max_streams, (unsigned)ns), 32, smem, st>>>(scans, scan_first + s0, *bufs, lut_cap);
+            acrefine_apply_kernel<<<dim3((max_blocks + 127) / 128, (unsigned)ns), 128, smem, st>>>(scans, scan_first + s0, *bufs, lut_cap);
+        }
     } else {
         return BJ_E_ARG;
     }

@@ -64,6 +64,10 @@ static int walk_one(const uint8_t* d, uint64_t n, bj_host_entry* out, int max_en
         pos = (uint64_t)(q - d);
         if (pos + 1 >= n) break;
         uint32_t m = d[pos + 1];
+        if (m == 0xFF) {  // fill byte in front of a marker (parser.py does the same)
+            pos += 1;
+            continue;
+        }
         pos += 2;
         if (m == 0x00 || (m >= 0xD0 && m <= 0xD7)) continue;
         if (k >= max_entries) return -2;

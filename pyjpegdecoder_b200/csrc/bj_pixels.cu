@@ -455,7 +455,16 @@ bj_status bj_pixels(const bj_image* images, int n_images, int max_strips, const 
                     uint64_t total_blocks, const int16_t* qtabs, const double* idct_table_t, void* out, int out_kind,
                     uint32_t layout_mask, uint32_t* stats, void* stream) {
     if (!images || n_images <= 0 || max_strips <= 0 || !in || !qtabs || !idct_table_t || !out) return BJ_E_ARG;
-    if (n_images > 65535) return BJ_E_ARG;
+    if (n_images > 65535) {
+        // the image index rides on grid.y: larger batches run as slices (image records hold absolute buffer offsets)
+        for (int i0 = 0; i0 < n_images; i0 += 65535) {
+            const int n = n_images - i0 < 65535 ? n_images - i0 : 65535;
+            bj_status st = bj_pixels(images + i0, n, max_strips, in, in_kind, total_blocks, qtabs, idct_table_t, out, out_kind,
+                                     layout_mask, stats, stream);
+            if (st != BJ_OK) return st;
+        }
+        return BJ_OK;
+    }
     if (in_kind != BJ_IN_COEF && in_kind != BJ_IN_SAMPLES) return BJ_E_ARG;
     if (out_kind < BJ_OUT_RGB || out_kind > BJ_OUT_CANVAS) return BJ_E_ARG;
     static_assert(sizeof(bj_image) == 72, "bj_image layout");

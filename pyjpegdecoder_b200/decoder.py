@@ -111,6 +111,51 @@ class JpegDecoder:
             self._image_array = np.swapaxes(self.image_tensor.cpu().numpy(), 0, 1)
         return self._image_array
 
+    # ---- hand-off to other consumers (the step after the path) -------------------------
+    def __dlpack__(self, stream=None):
+        """DLPack capsule of the (H, W, 3) / (H, W) uint8 device tensor: zero-copy hand-off to any DLPack consumer
+        (torch.from_dlpack, cupy.from_dlpack, jax, ...)."""
+        t = self.image_tensor
+        return t.__dlpack__(stream=stream) if stream is not None else t.__dlpack__()
+
+    def __dlpack_device__(self):
+        return self.image_tensor.__dlpack_device__()
+
+    @property
+    def __cuda_array_interface__(self):
+        """Numba / CuPy view of the device pixels ((H, W, 3) or (H, W), uint8, C order)."""
+        return self.image_tensor.__cuda_array_interface__
+
+    def save(self, path: Union[str, Path, None] = None) -> Path:
+        """Write the decoded image with Pillow (the reference's save(), jpeg_decoder.py:1485-1532, minus the Tk file
+        dialog): default `<input stem>.png` next to the input file, never overwriting (" (1)", " (2)", ... like the
+        reference), PNG when the suffix is not a format Pillow knows.  The pixels make one device->host copy through
+        pinned memory.  Returns the path written."""
+        from PIL import Image
+        if path is None:
+            if self.file_path is None:
+                raise ValueError("save() needs a path when the decoder was given bytes")
+            path = self.file_path.with_suffix(".png")
+        path = Path(path)
+        stem, count = path.stem, 1
+        while path.exists():
+            path = path.with_name(f"{stem} ({count}){path.suffix}")
+            count += 1
+        t = self.image_tensor
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t)
+        img = Image.fromarray(host.numpy())
+        try:
+            img.save(path)
+        except ValueError:
+            path = path.with_suffix(".png")
+            count = 1
+            while path.exists():
+                path = path.with_name(f"{stem} ({count}).png")
+                count += 1
+            img.save(path, format="png")
+        return path
+
     # ---- tables, in the reference's formats --------------------------------------------------------
     @property
     def quantization_tables(self) -> Dict[int, np.ndarray]:

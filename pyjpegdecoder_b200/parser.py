@@ -149,6 +149,9 @@ def parse_jpeg(data: bytes) -> ParsedJpeg:
         if pos < 0 or pos + 1 >= n:
             break                                                   # ran off the file (:79-83)
         m = data[pos + 1]
+        if m == 0xFF:                                               # fill byte before a marker (T.81 B.1.1.2): the
+            pos += 1                                                # reference would misread it as a segment; skip it
+            continue
         pos += 2
         if m == 0x00 or 0xD0 <= m <= 0xD7:                          # (:93)
             continue
@@ -203,6 +206,16 @@ def parse_jpeg(data: bytes) -> ParsedJpeg:
             q, ln = 0, len(seg)
             while q < ln:
                 dest = seg[q]
+                if dest >> 4 == 1:                                  # Pq = 1: 16-bit entries (the reference reads 64
+                    vals = seg[q + 1:q + 129]                       # bytes whatever Pq says, :443-454, and files the
+                    if len(vals) != 128:                            # table under the wrong id; here it is parsed)
+                        raise CorruptedJpeg("Failed to parse quantization tables.")
+                    t = np.frombuffer(vals, dtype=">u2").astype(np.int32)
+                    if (t > 32767).any():
+                        raise UnsupportedJpeg("Quantization table entries above 32767 are not supported.")
+                    p.qtables[dest & 15] = t.astype(np.int16)
+                    q += 129
+                    continue
                 vals = seg[q + 1:q + 65]
                 if len(vals) != 64:
                     raise CorruptedJpeg("Failed to parse quantization tables.")

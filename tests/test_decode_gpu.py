@@ -107,3 +107,25 @@ def test_corrupted_scans_never_poison_the_device():
     data, z = _case(name)
     d = decode_batch([data] * 4, device="cuda:0")[0]
     assert np.array_equal(d.image_array, z["rgb"])
+
+
+def test_output_consumers_dlpack_cuda_array_interface_and_save(tmp_path):
+    """The step after the path: zero-copy hand-off and save() (jpeg_decoder.py:1485-1532)."""
+    import torch
+    from PIL import Image
+    from pyjpegdecoder_b200 import JpegDecoder
+    data, z = _case("base_120x88_ss2")
+    src = tmp_path / "picture.jpg"
+    src.write_bytes(data)
+    d = JpegDecoder(src, device="cuda:0")
+    t = torch.from_dlpack(d)
+    assert t.is_cuda and t.data_ptr() == d.image_tensor.data_ptr()
+    assert np.array_equal(np.swapaxes(t.cpu().numpy(), 0, 1), z["rgb"])
+    cai = d.__cuda_array_interface__
+    assert cai["shape"] == tuple(d.image_tensor.shape) and cai["typestr"] == "|u1" and cai["data"][0] == d.image_tensor.data_ptr()
+    p1 = d.save()
+    p2 = d.save()
+    assert p1 == tmp_path / "picture.png" and p2 == tmp_path / "picture (1).png"
+    assert np.array_equal(np.swapaxes(np.array(Image.open(p1)), 0, 1), z["rgb"])
+    p3 = d.save(tmp_path / "out.unknownext")
+    assert p3.suffix == ".png" and p3.exists()
