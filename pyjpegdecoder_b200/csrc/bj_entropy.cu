@@ -39,6 +39,11 @@ constexpr int T = BJ_ENTROPY_THREADS;
 #endif
 constexpr int TW = BJ_WRITE_THREADS;  // subsequences per CTA of write_kernel (its LUT copy is amortised over more threads)
 constexpr int S = BJ_SUBSEQ_BITS;
+#ifndef BJ_WARM_BITS
+#define BJ_WARM_BITS BJ_SUBSEQ_BITS
+#endif
+constexpr int kWarm = BJ_WARM_BITS;  // bits decoded ahead of a subsequence to obtain its speculative entry state (<= S)
+static_assert(kWarm > 0 && kWarm <= S, "warm-up must not reach further back than one subsequence");
 constexpr int kMaxLutSmem = 12288;                  // most LUT entries ever staged in shared memory (48 KB)
 
 
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(T) spec_kernel(const bj_scan* __restrict__ sca
     else {
         uint64_t ex;
         SubCount k;  // nothing is counted while warming up (own_rel = 0xFFFFFFFF)
-        run_sub(sh, B, src, si.b0, 0xFFFFFFFFu, si.own_rel, si.end_rel, pack_state(si.own - S, z0, 0), ex, k);
+        run_sub(sh, B, src, si.b0, 0xFFFFFFFFu, si.own_rel, si.end_rel, pack_state(si.own - kWarm, z0, 0), ex, k);
         st = ex;
     }
     uint64_t ex;

@@ -21,39 +21,79 @@ constexpr int kTile = BJ_UNSTUFF_TILE;  // raw bytes per CTA
 constexpr int kThreads = kTile / 16;    // 16 bytes per thread
 constexpr uint64_t kByteMask = (1ull << 40) - 1;
 
+// Per-byte flags of a thread's 16 bytes, kept in the bit order the SWAR classification produces them in: byte i
+// (word k = i >> 2, byte j = i & 3 of that word) is bit 8 j + k.  Nothing ever needs them in natural order: counts are
+// popcounts, and the scatter loop tests a compile-time bit per byte.
+#define BJ_FLAG_BIT(i) (8 * ((i) & 3) + ((i) >> 2))
 struct Flags {
-    uint32_t keep;    // bit i: byte i of the thread's 16 is kept
-    uint32_t marker;  // bit i: byte i is the second byte of a restart marker
+    uint32_t keep;    // byte i is kept
+    uint32_t marker;  // byte i is the second byte of a restart marker
 };
 
-// Classify the 16 bytes starting at offset `off` of the 16-byte aligned region `seg`; the scan's
-// bytes are [lead, len) of that region (lead = raw_off & 15), everything else is dropped.
-__device__ __forceinline__ Flags classify(const uint8_t* __restrict__ seg, uint32_t off, uint32_t lead, uint32_t len,
-                                          uint4& data) {
-    Flags f{0u, 0u};
-    if (off >= len) {
-        data = make_uint4(0, 0, 0, 0);
-        return f;
-    }
-    data = __ldg(reinterpret_cast<const uint4*>(seg + off));
-    const uint8_t* b = reinterpret_cast<const uint8_t*>(&data);
-    uint32_t prev = (off > lead) ? __ldg(seg + off - 1) : 0u;
-    uint32_t nextblk = (off + 16 < len) ? __ldg(seg + off + 16) : 0u;
+// 0x80 in every byte of w that is zero (exact, no carries between bytes)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t w) { return ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w | 0x7F7F7F7Fu); }
+// the four per-word byte masks (0x80 per flagged byte) of a 16-byte chunk -> one word with byte i at bit BJ_FLAG_BIT(i)
+__device__ __forceinline__ uint32_t gather16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    return (m0 >> 7) | (m1 >> 6) | (m2 >> 5) | (m3 >> 4);
+}
+// flags of byte i moved to byte i + 1 (the flag of byte 15 falls out)
+__device__ __forceinline__ uint32_t next_byte(uint32_t f) { return ((f << 8) & 0x0F0F0F00u) | ((f >> 23) & 0x0Eu); }
+// flags of byte i moved to byte i - 1 (the flag of byte 0 falls out)
+__device__ __forceinline__ uint32_t prev_byte(uint32_t f) { return ((f >> 8) & 0x000F0F0Fu) | ((f & 0x0Eu) << 23); }
+// bytes [lo, hi) of the chunk, 0 <= lo <= hi <= 16
+__device__ __forceinline__ uint32_t range16(uint32_t lo, uint32_t hi) {
+    uint32_t f = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        uint32_t cur = b[i];
-        uint32_t nxt = (i < 15) ? (uint32_t)b[i + 1] : nextblk;
-        bool inside = off + i >= lead && off + i < len;
-        if (!inside) cur = 0u;
-        if (off + i + 1 >= len) nxt = 0u;
-        bool stuffed = (cur == 0u) && (prev == 0xFFu);
-        bool rst2 = (prev == 0xFFu) && ((cur & 0xF8u) == 0xD0u);
-        bool rst1 = (cur == 0xFFu) && ((nxt & 0xF8u) == 0xD0u);
-        if (inside && !stuffed && !rst2 && !rst1) f.keep |= 1u << i;
-        if (inside && rst2) f.marker |= 1u << i;
-        prev = cur;
-    }
+    for (int i = 0; i < 16; i++)
+        if ((uint32_t)i >= lo && (uint32_t)i < hi) f |= 1u << BJ_FLAG_BIT(i);
     return f;
+}
+
+// Classify the 16 bytes starting at offset `off` of the 16-byte aligned region `seg`; the scan's bytes are
+// [lead, len) of that region (lead = raw_off & 15), everything else is dropped.  Word-parallel: the three byte
+// classes that matter (0xFF, 0x00, RSTn's second byte 0xD0..0xD7) are found with carry-free byte tests on the four
+// words, everything else is mask arithmetic.  A kept byte is one that is inside the scan and is neither a stuffed
+// zero (previous byte 0xFF), nor the 0xFF or the second byte of a restart marker (jpeg_decoder.py:667-669, :676-677).
+// prev / next: the byte before / after the chunk (they come from the neighbouring lanes where possible).
+__device__ __forceinline__ Flags classify(uint4 data, uint32_t off, uint32_t lead, uint32_t len, uint32_t prev, uint32_t next) {
+    Flags f{0u, 0u};
+    if (off >= len) return f;
+    const uint32_t w[4] = {data.x, data.y, data.z, data.w};
+    const uint32_t lo = lead > off ? lead - off : 0u, hi = len - off < 16u ? len - off : 16u;
+    const uint32_t inside = (lo == 0u && hi == 16u) ? 0x0F0F0F0Fu : range16(lo, hi);
+    uint32_t ffm[4], zm[4], rm[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        ffm[k] = zero_bytes(~w[k]);
+        zm[k] = zero_bytes(w[k]);
+        rm[k] = zero_bytes((w[k] & 0xF8F8F8F8u) ^ 0xD0D0D0D0u);
+    }
+    const uint32_t ff = gather16(ffm[0], ffm[1], ffm[2], ffm[3]) & inside;
+    const uint32_t zero = gather16(zm[0], zm[1], zm[2], zm[3]) & inside;
+    const uint32_t rst = gather16(rm[0], rm[1], rm[2], rm[3]) & inside;
+    const bool prev_ff = (off > lead) && prev == 0xFFu;
+    const bool next_rst = (off + 16u < len) && (next & 0xF8u) == 0xD0u;
+    const uint32_t after_ff = next_byte(ff) | (prev_ff ? 1u : 0u);                       // bytes that follow a 0xFF
+    const uint32_t before_rst = prev_byte(rst) | (next_rst ? (1u << BJ_FLAG_BIT(15)) : 0u);  // bytes followed by D0..D7
+    const uint32_t stuffed = after_ff & zero;
+    const uint32_t rst2 = after_ff & rst;
+    const uint32_t rst1 = ff & before_rst;
+    f.keep = inside & ~(stuffed | rst2 | rst1);
+    f.marker = rst2;
+    return f;
+}
+
+// The chunk of a thread plus the bytes around it: neighbours inside the warp hand them over with shuffles, the warp's
+// first and last lanes read them from memory.
+__device__ __forceinline__ Flags load_classify(const uint8_t* __restrict__ seg, uint32_t off, uint32_t lead, uint32_t len, uint4& data) {
+    const int lane = threadIdx.x & 31;
+    data = make_uint4(0, 0, 0, 0);
+    if (off < len) data = __ldg(reinterpret_cast<const uint4*>(seg + off));
+    uint32_t prev = __shfl_up_sync(0xffffffffu, data.w >> 24, 1);
+    uint32_t next = __shfl_down_sync(0xffffffffu, data.x & 0xFFu, 1);
+    if (lane == 0) prev = (off > lead && off < len) ? (uint32_t)__ldg(seg + off - 1) : 0u;
+    if (lane == 31) next = (off + 16u < len) ? (uint32_t)__ldg(seg + off + 16) : 0u;
+    return classify(data, off, lead, len, prev, next);
 }
 
 __global__ void __launch_bounds__(kThreads) unstuff_count_kernel(const uint8_t* __restrict__ raw,
@@ -65,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) unstuff_count_kernel(const uint8_t* 
     const uint32_t off = (tile - sc.tile0) * kTile + threadIdx.x * 16;
     const uint32_t lead = (uint32_t)(sc.raw_off & 15);
     uint4 d;
-    Flags f = classify(raw + (sc.raw_off & ~15ull), off, lead, lead + sc.raw_len, d);
+    Flags f = load_classify(raw + (sc.raw_off & ~15ull), off, lead, lead + sc.raw_len, d);
     uint64_t v = (uint64_t)__popc(f.keep) | ((uint64_t)__popc(f.marker) << 40);
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -120,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) unstuff_scatter_kernel(const uint8_t
     const uint32_t off = (tile - sc.tile0) * kTile + threadIdx.x * 16;
     const uint32_t lead = (uint32_t)(sc.raw_off & 15);
     uint4 d;
-    Flags f = classify(raw + (sc.raw_off & ~15ull), off, lead, lead + sc.raw_len, d);
+    Flags f = load_classify(raw + (sc.raw_off & ~15ull), off, lead, lead + sc.raw_len, d);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // exclusive prefix of (kept, markers) over the CTA
     uint32_t nk = __popc(f.keep), nm = __popc(f.marker);
@@ -147,8 +187,8 @@ __global__ void __launch_bounds__(kThreads) unstuff_scatter_kernel(const uint8_t
     uint32_t k = my_k, m = my_m;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        if (f.keep & (1u << i)) sbuf[shift + k++] = b[i];
-        if (f.marker & (1u << i)) {
+        if (f.keep & (1u << BJ_FLAG_BIT(i))) sbuf[shift + k++] = b[i];
+        if (f.marker & (1u << BJ_FLAG_BIT(i))) {
             uint64_t ord = mbase + m++ + 1;  // stream that starts right after this marker
             if (ord < sc.n_streams) stream_start[sc.stream0 + ord] = obase + k;
         }
