@@ -625,25 +625,27 @@ __device__ __forceinline__ uint64_t block_mask(const uint4 (&v)[8]) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-// One warp per stream.  All lanes stage the masks of the next 32 blocks (their loads are issued before
-// lane 0 parses the current chunk, so the memory latency is off the sequential path); lane 0 parses;
-// all lanes store the start positions.
+// One warp per stream.  The warp pre-decodes a window of the bitstream (one candidate symbol per bit position, all
+// lanes), stages the masks of the next 32 blocks (their loads are issued one chunk ahead), turns them into the
+// per-block landing tables, then lane 0 chases the chain through window and tables (bj_entropy.cuh) and all lanes
+// store the start positions.  The window is rebuilt whenever the next block could run past its end.
 __global__ void __launch_bounds__(32) acrefine_parse_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
-                                                            uint32_t lut_cap) {
+                                                            uint32_t lut_cap, uint32_t win_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
+    // the pre-decoded window follows the LUT in dynamic shared memory: win_bits entries (the host picks a small window
+    // for waves with many short streams -- restart intervals -- so that many of these one-warp CTAs fit an SM)
+    uint32_t* const s_pre = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(CtaShared) + sizeof(uint32_t) * lut_cap + 15) & ~(size_t)15));
     __shared__ __align__(4) uint8_t s_tab[32 * BJ_ACR_TAB_STRIDE];
     __shared__ uint32_t s_pos[32];
-    __shared__ uint32_t s_err;
+    __shared__ uint32_t s_state[4];   // pos, eob_run, next block, err (lane 0 -> warp)
     load_scan(sh, scans, scan_first + blockIdx.y, B, lut_cap);
     const bj_scan& sc = sh.sc;
     const uint32_t m = blockIdx.x;
     if (m >= sc.n_streams) return;
     const int lane = threadIdx.x;
     GlobalSrc src{B.words, (uint32_t)B.words_len};
-    DeepReader<GlobalSrc> rd;
     const uint64_t sb0 = B.stream_start[sc.stream0 + m] * 8, sb1 = B.stream_end[sc.stream0 + m] * 8;
-    rd.seek(&src, sb0);
     const uint32_t end_rel = (uint32_t)(sb1 - sb0);
     const uint32_t mcu0 = m * sc.ri;
     const uint32_t nblk = min(sc.ri, sc.n_mcu - mcu0);
@@ -651,7 +653,17 @@ __global__ void __launch_bounds__(32) acrefine_parse_kernel(const bj_scan* __res
     const uint32_t* gtab = B.lut + sc.lut_off + sh.ctx.ac_tab[0];
     const uint32_t* stab = sh.lut + sh.ctx.ac_tab[0];
     const int ss = sh.ctx.ss, se = sh.ctx.se;
-    uint32_t eob_run = 0;
+    uint32_t win_base = 0;
+    auto build_window = [&](uint32_t base) {
+        win_base = base;
+        // positions past the end of the stream (+ slack for a corrupt tail) are never visited
+        const uint32_t n = min(win_bits, end_rel + 64u > base ? end_rel + 64u - base : 0u);
+        if (ls) for (uint32_t k = lane; k < n; k += 32) s_pre[k] = acrefine_predecode(src, sb0 + base + k, stab);
+        else for (uint32_t k = lane; k < n; k += 32) s_pre[k] = acrefine_predecode(src, sb0 + base + k, gtab);
+        __syncwarp();
+    };
+    build_window(0);
+    uint32_t pos = 0, eob_run = 0;
     uint4 v[8];
     size_t addr = 0, addr_next = 0;
     if ((uint32_t)lane < nblk) {
@@ -667,13 +679,23 @@ __global__ void __launch_bounds__(32) acrefine_parse_kernel(const bj_scan* __res
             load_block(B.coef + addr_next * 64, v);
         }
         __syncwarp();
-        if (lane == 0) {
-            if (ls) s_err = acrefine_parse_chunk(rd, sh.ctx, stab, end_rel, s_tab, nb, eob_run, s_pos);
-            else s_err = acrefine_parse_chunk(rd, sh.ctx, gtab, end_rel, s_tab, nb, eob_run, s_pos);
+        int i = 0;
+        uint32_t err = 0;
+        while (i < nb) {
+            if (pos > win_base + (win_bits - BJ_ACR_WIN_SLACK)) build_window(pos);
+            if (lane == 0) {
+                uint32_t e = 0;
+                const int i2 = acrefine_parse_window(s_pre, win_base, win_base + (win_bits - BJ_ACR_WIN_SLACK), sh.ctx,
+                                                     end_rel, s_tab, i, nb, pos, eob_run, s_pos, e);
+                s_state[0] = pos; s_state[1] = eob_run; s_state[2] = (uint32_t)i2; s_state[3] = e;
+            }
+            __syncwarp();
+            pos = s_state[0]; eob_run = s_state[1]; i = (int)s_state[2]; err = s_state[3];
+            __syncwarp();
+            if (err) break;
         }
-        __syncwarp();
-        if (s_err) {
-            if (lane == 0) atomicOr(&B.err[sc.image], s_err);
+        if (err) {
+            if (lane == 0) atomicOr(&B.err[sc.image], err);
             // blocks that were not reached decode nothing: an end-of-band block at the end of the stream
             for (uint32_t b = cb + lane; b < nblk; b += 32)
                 B.blk_pos[block_address(sc, mcu0 + b, 0)] = end_rel | BJ_ACR_IN_EOBRUN;
@@ -777,12 +799,16 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
         }
     } else if (mode == BJ_MODE_AC_REFINE) {
         if (!bufs->blk_pos || max_streams == 0 || max_blocks == 0) return BJ_E_ARG;
-        e = cudaFuncSetAttribute(acrefine_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // window of the sequential parse: large for long streams (fewer rebuilds), small when the wave consists of many
+        // short streams (restart intervals): their one-warp CTAs then fit an SM by the dozen
+        const uint32_t win_bits = max_streams > 32u ? 4096u : (uint32_t)BJ_ACR_WIN_BITS;
+        const size_t parse_smem = ((smem + 15) & ~(size_t)15) + sizeof(uint32_t) * win_bits;
+        e = cudaFuncSetAttribute(acrefine_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)parse_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(acrefine_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return bj_set_cuda_error(e, "bj_entropy_decode/attr");
         for (int s0 = 0; s0 < n_scans; s0 += 65535) {
             const int ns = n_scans - s0 < 65535 ? n_scans - s0 : 65535;
-            acrefine_parse_kernel<<<dim3(max_streams, (unsigned)ns), 32, smem, st>>>(scans, scan_first + s0, *bufs, lut_cap);
+            acrefine_parse_kernel<<<dim3(max_streams, (unsigned)ns), 32, parse_smem, st>>>(scans, scan_first + s0, *bufs, lut_cap, win_bits);
             acrefine_apply_kernel<<<dim3((max_blocks + 127) / 128, (unsigned)ns), 128, smem, st>>>(scans, scan_first + s0, *bufs, lut_cap);
         }
     } else {

@@ -511,84 +511,106 @@ BJ_HD void acrefine_build_table(uint64_t m, int ss, int se, uint8_t* t) {
     t[BJ_ACR_TAB_NZ] = (uint8_t)popc64(m & (~0ull << ss) & (~0ull >> (63 - se)));
 }
 
-// Bit reader with one more word of look-ahead than BitReader: the word fetched at a refill is not
-// needed before the refill after it, which keeps the fetch latency off the parse's dependency chain.
-template <class Src>
-struct DeepReader {
-    const Src* src;
-    uint32_t w0, w1, w2;
-    int o;
-    uint32_t next, rel;
-    BJ_HDM void seek(const Src* s, uint64_t base_bit) {
-        src = s;
-        rel = 0;
-        uint32_t w = (uint32_t)(base_bit >> 5);
-        o = (int)(base_bit & 31);
-        w0 = src->word(w);
-        w1 = src->word(w + 1);
-        w2 = src->word(w + 2);
-        next = w + 3;
-    }
-    BJ_HDM uint32_t peek32() const { return funnel_left(w0, w1, o); }
-    BJ_HDM void skip(uint32_t n) {  // any n
-        o += (int)n;
-        rel += n;
-        while (o >= 32) {
-            o -= 32;
-            w0 = w1;
-            w1 = w2;
-            w2 = src->word(next++);
-        }
-    }
-};
+// ---- the sequential parse over a PRE-DECODED WINDOW -----------------------------------------------------
+// What makes the parse slow is not the work but the length of the dependency chain per symbol (one lane, every
+// instruction at full latency).  Everything that depends only on the BIT POSITION is therefore taken off the chain:
+// the warp decodes the Huffman symbol that WOULD start at each of the next BJ_ACR_WIN_BITS bit positions, all in
+// parallel, into a shared-memory window (acrefine_predecode: code length + sign bit, run, EOBn with its run count).
+// The chain that is left per symbol is: window entry at the current position -> landing position from the block's
+// table (depends on the run) -> next position.  Two dependent shared-memory loads and a handful of integer
+// operations instead of a funnel shift, a two-level LUT walk, field extraction and the refill logic.
+#ifndef BJ_ACR_WIN_BITS
+#define BJ_ACR_WIN_BITS 8192
+#endif
+// A block that starts inside [window start, window start + BJ_ACR_WIN_BITS - BJ_ACR_WIN_SLACK] has all its symbol
+// starts inside the window: at most 64 symbols (each lands on a new coefficient) of at most 16 + 1 bits, 63
+// correction bits, one EOBn of 16 + 14 bits.
+#define BJ_ACR_WIN_SLACK 1280
+#define BJ_ACR_E_EOB 0x1000u   // entry: end of band (bits 16..31: blocks the run still covers AFTER this one)
+#define BJ_ACR_E_BAD 0x2000u   // entry: not a code, or a size other than 0 / 1 (ends the block, flags the stream)
 
-// Parse pass over a chunk of nb consecutive blocks: tabs + i * BJ_ACR_TAB_STRIDE = table of block i;
-// pos[i] receives where block i starts (relative bit position | BJ_ACR_IN_EOBRUN).
+// Window entry for the symbol that starts at absolute bit `abs_bit`: bits 0..7 = bits consumed by code + sign (or
+// + EOBRUN bits), bits 8..11 = run.
 template <class Src>
-BJ_HD uint32_t acrefine_parse_chunk(DeepReader<Src>& rd, const ScanCtx& c, const uint32_t* tab, uint32_t end_rel,
-                                    const uint8_t* tabs, int nb, uint32_t& eob_run, uint32_t* pos) {
-    // Written for the shortest dependency chain per symbol (this loop runs on ONE lane, every instruction on the
-    // chain costs its full latency): no early exits inside a block -- problems are collected in sticky flags and
-    // looked at once per block; a bad code consumes one bit and ends the block like an EOB, a run past the last
-    // zero-history coefficient (table entry 0xFF >= se) ends the block too.
+BJ_HD uint32_t acrefine_predecode(const Src& src, uint64_t abs_bit, const uint32_t* tab) {
+    const uint32_t w = (uint32_t)(abs_bit >> 5);
+    const uint32_t pk = funnel_left(src.word(w), src.word(w + 1), (int)(abs_bit & 31));
+    const uint32_t e = lut_lookup(tab, pk >> 16);
+    const int L = ent_len(e), rs = ent_sym(e);
+    const int r = rs >> 4, s = rs & 15;
+    if (L == 0 || s > 1) return 1u | BJ_ACR_E_EOB | BJ_ACR_E_BAD;   // consumes one bit, ends the block like EOB0
+    if (s == 0 && r != 15) {                                         // EOBn (:1144-1149); EOB0 is a run of one block
+        const uint32_t run = (1u << r) + (r ? take_bits(pk, L, r) : 0u) - 1u;
+        return (uint32_t)(L + r) | BJ_ACR_E_EOB | (run << 16);
+    }
+    return (uint32_t)(L + s) | ((uint32_t)r << 8);
+}
+
+// Parse blocks [i0, nb) of a chunk (tables at tabs + i * BJ_ACR_TAB_STRIDE) from bit position `pos` (relative to the
+// stream start) while they start at or before win_limit; pre[k] = entry of position win_base + k.  blkpos[i]
+// receives where block i starts (| BJ_ACR_IN_EOBRUN).  Returns the index of the first block NOT parsed; err != 0
+// stops the stream.  Written for the shortest dependency chain: no early exits inside a block, problems are
+// collected in sticky flags and looked at once per block; a run past the last zero-history coefficient (table
+// entry 0xFF >= se) ends the block.
+BJ_HD int acrefine_parse_window(const uint32_t* pre, uint32_t win_base, uint32_t win_limit, const ScanCtx& c, uint32_t end_rel,
+                                const uint8_t* tabs, int i0, int nb, uint32_t& pos, uint32_t& eob_run, uint32_t* blkpos,
+                                uint32_t& err) {
     const int ss = c.ss, se = c.se;
     uint32_t bad_code = 0, bad_index = 0;
-    for (int i = 0; i < nb; i++) {
+    int i = i0;
+    // the chain runs on p = position inside the window (an index into pre[]); pos = win_base + p
+    if (win_base > end_rel + 7u) {   // the window itself starts past the end of the stream
+        err = BJ_ERR_OVERRUN;
+        return i0;
+    }
+    uint32_t p = pos - win_base;
+    const uint32_t p_limit = win_limit - win_base, p_end = end_rel + 7u - win_base;
+    for (; i < nb; i++) {
+        if (p > p_limit) break;
         const uint8_t* t = tabs + i * BJ_ACR_TAB_STRIDE;
-        if (rd.rel > end_rel + 7) return BJ_ERR_OVERRUN;
+        if (p > p_end) {
+            err = BJ_ERR_OVERRUN;
+            pos = win_base + p;
+            return i;
+        }
         if (eob_run) {
-            pos[i] = rd.rel | BJ_ACR_IN_EOBRUN;
-            rd.skip(t[BJ_ACR_TAB_NZ]);
+            blkpos[i] = (win_base + p) | BJ_ACR_IN_EOBRUN;
+            p += t[BJ_ACR_TAB_NZ];
             eob_run--;
             continue;
         }
-        pos[i] = rd.rel;
+        blkpos[i] = win_base + p;
         int j = 0;     // zero-history coefficients consumed
         int cd = ss;   // ss + non-zero coefficients refined so far
-        bool more;
-        do {
-            const uint32_t pk = rd.peek32();
-            const uint32_t e = lut_lookup(tab, pk >> 16);
-            const int L = ent_len(e), rs = ent_sym(e);
-            const int r = rs >> 4;
-            bad_code |= (L == 0) ? 1u : 0u;
-            if ((rs & 15) == 0 && r != 15) {  // EOBn (an invalid entry decodes as EOB0 of one bit)
-                eob_run = (1u << r) + (r ? take_bits(pk, L, r) : 0u) - 1u;
-                rd.skip((uint32_t)(ent_total(e) + r + (int)t[BJ_ACR_TAB_NZ] - (cd - ss)));
+        for (;;) {
+            // the chain: window entry -> run -> table entry -> next position.  Nothing else may sit on it: a run past
+            // the last zero-history coefficient (table entry 0xFF) makes p meaningless, but it also ends the block
+            // (0xFF >= se) and is reported right after it.
+            const uint32_t e = pre[p];
+            if (e & BJ_ACR_E_EOB) {
+                bad_code |= e & BJ_ACR_E_BAD;
+                eob_run = e >> 16;
+                p += (e & 0xFFu) + (uint32_t)((int)t[BJ_ACR_TAB_NZ] - (cd - ss));
                 break;
             }
-            const int tt = j + r;  // ZRL: the 16th zero from here (r = 15)
+            const int tt = j + (int)byte_of(e, 1);          // ZRL: the 16th zero from here (run 15)
             const int zp = t[tt];
-            const int base = ent_total(e) - tt - cd;  // ready before the table value arrives
-            bad_index |= (zp == 0xFF) ? 1u : 0u;
-            more = zp < se;
-            rd.skip((uint32_t)(base + (more || zp != 0xFF ? zp : tt + cd)));
+            p += (uint32_t)((int)byte_of(e, 0) - tt - cd + zp);  // code + sign bits, then one correction bit per non-zero passed
             cd = zp - tt;
             j = tt + 1;
-        } while (more);
-        if (bad_code | bad_index) return bad_code ? BJ_ERR_BAD_CODE : BJ_ERR_COEF_INDEX;
+            if (zp >= se) {
+                bad_index |= (zp == 0xFF) ? 1u : 0u;
+                break;
+            }
+        }
+        if (bad_code | bad_index) {
+            err = bad_code ? BJ_ERR_BAD_CODE : BJ_ERR_COEF_INDEX;
+            pos = win_base + p;
+            return i;
+        }
     }
-    return 0;
+    pos = win_base + p;
+    return i;
 }
 
 }  // namespace bj

@@ -208,17 +208,27 @@ uint32_t hs_acrefine_stream(const uint32_t* words, uint64_t n_words, uint64_t st
     const uint32_t* tab = ss_->lut + c.ac_tab[0];
     const uint32_t end_rel = (uint32_t)((end_byte - start_byte) * 8);
     std::vector<uint32_t> pos(nblk_stream);
-    {
-        DeepReader<HostSrc> rd;
-        rd.seek(&src, start_byte * 8);
-        uint32_t eob_run = 0;
+    {   // the device's orchestration: pre-decoded window, rebuilt whenever the next block could run out of it
+        std::vector<uint32_t> pre(BJ_ACR_WIN_BITS);
+        uint32_t win_base = 0, pos_bits = 0, eob_run = 0;
+        auto build = [&](uint32_t base) {
+            win_base = base;
+            for (uint32_t k = 0; k < BJ_ACR_WIN_BITS; k++) pre[k] = acrefine_predecode(src, start_byte * 8 + base + k, tab);
+        };
+        build(0);
         for (uint32_t cb = 0; cb < nblk_stream; cb += 32) {
             int nb = (int)std::min<uint32_t>(32, nblk_stream - cb);
             uint8_t tabs[32 * BJ_ACR_TAB_STRIDE];
             for (int i = 0; i < nb; i++)
                 acrefine_build_table(nonzero_mask(coef + (size_t)(cb + i) * 64), c.ss, c.se, tabs + i * BJ_ACR_TAB_STRIDE);
-            uint32_t err = acrefine_parse_chunk(rd, c, tab, end_rel, tabs, nb, eob_run, pos.data() + cb);
-            if (err) return err;
+            int i = 0;
+            while (i < nb) {
+                if (pos_bits > win_base + BJ_ACR_WIN_BITS - BJ_ACR_WIN_SLACK) build(pos_bits);
+                uint32_t err = 0;
+                i = acrefine_parse_window(pre.data(), win_base, win_base + BJ_ACR_WIN_BITS - BJ_ACR_WIN_SLACK, c, end_rel, tabs, i,
+                                          nb, pos_bits, eob_run, pos.data() + cb, err);
+                if (err) return err;
+            }
         }
     }
     uint32_t err = 0;
