@@ -53,7 +53,133 @@ struct GlobalSrc {
     // clamped, not branched: the buffer ends with 64 words of slack, a valid stream never reads past them, and what a
     // corrupt one reads there does not matter as long as it is deterministic
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return __ldg(gw + min(i, gn - 1u)); }
+    __device__ __forceinline__ void start(uint32_t) const {}
 };
+
+// ---- bitstream staging by a producer warp (write_kernel) ------------------------------------------------
+// Every lane of a decoding warp walks its own subsequence, so with 32 lanes refilling their bit windows at different
+// symbols some lane misses in (the small) L1 in practically every iteration of the symbol loop and the whole warp
+// waits an L2 round trip for it: 42 % of write_kernel's stall samples sat on the first use of the refilled word
+// (profiles/r2_full_summary.csv).  A register prefetch cannot hide that (ptxas copies the loop-carried window words at
+// the loop head, which reads the load's destination in the same iteration), and per-lane cp.async completion does not
+// exist in hardware: wait_group counts per WARP and the mbarrier form of the arrival wants a uniform address.  So one
+// extra warp per CTA -- always converged -- copies the bitstream for the decoding threads: 16-byte groups with
+// cp.async into a ring of kRing groups per decoding thread, driven by two words of shared memory per thread
+// (cons: the group the thread is reading; fill: every group below it has landed).  The decoding threads only ever
+// issue LDS.
+#ifndef BJ_RING
+#define BJ_RING 2
+#endif
+#ifndef BJ_PRODUCER_SLEEP
+#define BJ_PRODUCER_SLEEP 6000
+#endif
+constexpr int kRing = BJ_RING;  // groups per decoding thread (a power of two)
+constexpr uint32_t kConsIdle = 0xFFFFFFFEu, kConsDone = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t lds_volatile(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_volatile(uint32_t a, uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+// The decoding threads use the weak forms inside `asm volatile` (one access per call, in program order, but no
+// .volatile in the PTX): ptxas gives up the reconvergence points of a loop that contains a volatile access -- it
+// could be one half of an inter-thread hand-shake -- and the lanes of write_kernel then run their symbol loops and
+// block flushes one or two at a time (measured: 2.9x the executed warp instructions).
+__device__ __forceinline__ uint32_t lds_weak(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_weak(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+
+template <int NT>
+struct StagedSrc {
+    uint32_t ring;   // shared-space address of this thread's ring: kRing groups of 16 bytes, contiguous
+    uint32_t flags;  // shared-space address of cons[t]; fill[t] at flags + NT * 4
+    const uint32_t* gw;
+    uint32_t gn;
+    mutable uint32_t ready;  // the group being read has landed in the ring (a full register: a bool gets packed)
+    // No waiting anywhere: a group that has not landed yet (the first one or two of a thread, before the producer has
+    // seen it) is read from global memory instead.
+    __device__ __forceinline__ void enter(uint32_t i) const {  // i = first word of the group
+        sts_weak(flags, i);
+        ready = lds_weak(flags + NT * 4) > i ? 1u : 0u;
+    }
+    __device__ __forceinline__ void start(uint32_t w) const { enter(w & ~3u); }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const {
+        if ((i & 3u) == 0u) enter(i);
+        if (BJ_UNLIKELY(!ready)) return __ldg(gw + min(i, gn - 1u));
+        return lds_weak(ring + ((i & (4u * kRing - 1u)) << 2));
+    }
+    __device__ __forceinline__ void done() const { sts_weak(flags, kConsDone); }
+};
+
+// shared memory of the staging: NT * (kRing * 4 + 2) words, 16-byte aligned
+template <int NT>
+__device__ __forceinline__ StagedSrc<NT> staged_src(uint32_t* stage, int t, const uint32_t* gw, uint32_t gn) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(stage);
+    return StagedSrc<NT>{base + 16u * kRing * t, base + NT * kRing * 16 + 4u * t, gw, gn, 0u};
+}
+template <int NT>
+__device__ __forceinline__ void staged_init(uint32_t* stage, int tid, int nthreads) {
+    for (int i = tid; i < NT; i += nthreads) {
+        stage[NT * kRing * 4 + i] = kConsIdle;
+        stage[NT * kRing * 4 + NT + i] = 0u;
+    }
+}
+
+// The producer warp: lane l serves the decoding threads l, l + 32, ...  Runs until all of them are done.
+// cons[t] = first word of the group thread t is reading; fill[t] = every word below it has landed.
+template <int NT>
+__device__ __forceinline__ void staged_producer(uint32_t* stage, const uint32_t* __restrict__ gw, uint32_t gmax, int lane) {
+    constexpr int PER = NT / 32;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t cons0 = base + NT * kRing * 16, fill0 = cons0 + NT * 4;
+    uint32_t req[PER];  // next group to request for each of my threads (valid once the thread has started)
+    bool live[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        req[k] = 0;
+        live[k] = false;
+    }
+    for (;;) {
+        bool all_done = true, issued = false;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int t = lane + 32 * k;
+            const uint32_t cw = lds_volatile(cons0 + 4u * t);
+            if (cw == kConsDone) continue;
+            all_done = false;
+            if (cw == kConsIdle) continue;
+            const uint32_t c = cw >> 2;
+            if (!live[k]) {
+                live[k] = true;
+                req[k] = c;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {  // at most two groups per thread and round
+                if (req[k] < c + kRing) {
+                    const uint32_t* p = gw + 4 * (size_t)min(req[k], gmax);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (t * kRing + (req[k] & (kRing - 1))) * 16u), "l"(p) : "memory");
+                    req[k]++;
+                    issued = true;
+                }
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, all_done)) break;
+        if (__any_sync(0xFFFFFFFFu, issued)) {
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;\n\tfence.acq_rel.cta;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < PER; k++)
+                if (live[k]) sts_volatile(fill0 + 4u * (lane + 32 * k), req[k] << 2);
+        }
+        // One round every few microseconds is plenty (a decoding thread takes ~20 us per group; one that is faster
+        // than the producer reads that group from global memory) and keeps the producer's polling out of the issue
+        // slots of the decoding warps: 2 us -> 2.04 ms, 4 us -> 1.97, 8 us -> 1.96, 16 us -> 2.11 per 512 images.
+        __nanosleep(BJ_PRODUCER_SLEEP);
+    }
+}
 
 // Per-CTA scan context + the scan's Huffman LUTs (the bitstream itself is read through L1)
 struct CtaShared {
@@ -531,22 +657,31 @@ struct GlobalCoefSink {  // progressive first scans: single coefficient stores
     }
 };
 
-__global__ void __launch_bounds__(TW) write_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
-                                                  uint32_t lut_cap) {
+__global__ void __launch_bounds__(TW + 32) write_kernel(const bj_scan* __restrict__ scans, int scan_first, bj_entropy_buffers B,
+                                                       uint32_t lut_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared& sh = *reinterpret_cast<CtaShared*>(smem_raw);
     __shared__ __align__(16) uint32_t s_blocks[TW * 32];
+    __shared__ __align__(16) uint32_t s_stage[TW * (kRing * 4 + 2)];
     load_scan(sh, scans, scan_first + blockIdx.x, B, lut_cap);
     const uint32_t base = blockIdx.y * TW;
     if (base >= sh.scan_nsub) return;
     const int tid = threadIdx.x;
+    for (int i = tid; i < TW * 32; i += TW + 32) s_blocks[i] = 0u;
+    staged_init<TW>(s_stage, tid, TW + 32);
+    __syncthreads();
+    if (tid >= TW) {  // the producer warp
+        staged_producer<TW>(s_stage, B.words, (uint32_t)(B.words_len >> 2) - 1u, tid - TW);
+        return;
+    }
+    typedef StagedSrc<TW> SrcT;
+    const SrcT src = staged_src<TW>(s_stage, tid, B.words, (uint32_t)B.words_len);
     const uint32_t lscan = base + tid;
     SubInfo si = locate(sh, B, lscan);
-    for (int i = tid; i < TW * 32; i += TW) s_blocks[i] = 0u;
-    __syncthreads();
-    if (!si.valid) return;
-    GlobalSrc src{B.words, (uint32_t)B.words_len};
-    typedef GlobalSrc SrcT;
+    if (!si.valid) {
+        src.done();
+        return;
+    }
     const size_t g = (size_t)sh.sc.sub0 + lscan;
     const uint64_t st = B.sub_entry[g];
     const uint4 pre = reinterpret_cast<const uint4*>(B.sub_prefix)[g];
@@ -573,6 +708,7 @@ __global__ void __launch_bounds__(TW) write_kernel(const bj_scan* __restrict__ s
         if (ls) err = acfirst_run<true>(rd, z, sh.ctx, sh.lut, si.own_rel, si.stop_rel, si.end_rel, blk, si.nblk_stream, adv, sink);
         else err = acfirst_run<true>(rd, z, sh.ctx, glut, si.own_rel, si.stop_rel, si.end_rel, blk, si.nblk_stream, adv, sink);
     }
+    src.done();
     // the last subsequence of a stream checks that the stream held all its blocks
     if (si.stop == si.b1) {
         uint4 c = reinterpret_cast<const uint4*>(B.sub_count)[g];
@@ -786,7 +922,7 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
                                                                                                          bitmap_words, chain_lut);
         }
         if (phases & BJ_PHASE_WRITE) {
-            write_kernel<<<dim3((unsigned)n_scans, (max_sub + TW - 1) / TW), TW, smem, st>>>(scans, scan_first, *bufs, lut_cap);
+            write_kernel<<<dim3((unsigned)n_scans, (max_sub + TW - 1) / TW), TW + 32, smem, st>>>(scans, scan_first, *bufs, lut_cap);
         }
     } else if (mode == BJ_MODE_DC_REFINE) {
         unsigned gx = (max_blocks + 255) / 256;

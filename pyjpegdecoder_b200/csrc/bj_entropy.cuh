@@ -113,6 +113,7 @@ struct BitReader {
         const uint64_t p = base_bit + rel_bit;
         uint32_t w = (uint32_t)(p >> 5);
         o = (int)(p & 31);
+        src->start(w);
         w0 = src->word(w);
         w1 = src->word(w + 1);
         w2 = src->word(w + 2);

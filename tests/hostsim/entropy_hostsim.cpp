@@ -14,6 +14,7 @@ struct HostSrc {
     const uint32_t* w;
     uint64_t n;
     uint32_t word(uint32_t i) const { return i < n ? w[i] : 0xFFFFFFFFu; }
+    void start(uint32_t) const {}
 };
 
 extern "C" {
