@@ -203,6 +203,8 @@ bj_status bj_entropy_plan(const bj_scan* scans, int scan_first, int n_scans, con
 #define BJ_PHASE_FIX 2
 #define BJ_PHASE_WRITE 4
 #define BJ_PHASE_ALL 7
+#define BJ_PHASE_NO_BITMAP 8 /* testing: the chain step finds stream heads by binary search, the path it takes by
+                                itself for a scan of more than 262144 subsequences (128 MB of entropy-coded data) */
 bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, int mode, uint32_t max_sub,
                             uint32_t max_streams, uint32_t max_blocks, uint32_t max_lut,
                             const bj_entropy_buffers* bufs, uint32_t* chain, int phases, void* stream);

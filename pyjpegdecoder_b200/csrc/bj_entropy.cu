@@ -916,7 +916,7 @@ bj_status bj_entropy_decode(const bj_scan* scans, int scan_first, int n_scans, i
             // shared-memory bitmap of stream heads: one bit per subsequence of the largest scan, up to 32 KB
             // (with the 8 KB of LUT and the static arrays this stays below the 48 KB default limit)
             uint32_t bitmap_words = (max_sub + 31) / 32;
-            if (bitmap_words > 8192u) bitmap_words = 0;
+            if (bitmap_words > 8192u || (phases & BJ_PHASE_NO_BITMAP)) bitmap_words = 0;
             const uint32_t chain_lut = lut_cap <= 2048u ? lut_cap : 2048u;  // bitmap + LUT stay below the 48 KB default limit
             chain_kernel<<<n_scans, kChainThreads, (bitmap_words + chain_lut) * sizeof(uint32_t), st>>>(scans, scan_first, n_scans, *bufs,
                                                                                                          bitmap_words, chain_lut);

@@ -186,18 +186,26 @@ BATCH_CHUNK = 512
 
 
 def decode_batch(files: Sequence[Union[str, Path, bytes]], device: Optional[Union[str, torch.device]] = None,
-                 chunk: Optional[int] = None) -> List[JpegDecoder]:
+                 chunk: Optional[int] = None, on_error: str = "raise") -> List[JpegDecoder]:
     """Decode many files and return one JpegDecoder-like object per file (pixels stay on the device until
     `image_array` is read).  Small batches run as ONE device pipeline (one launch sequence for all files); batches
     larger than 1.5 x `chunk` files are cut into sub-batches of `chunk` files that flow through the streaming front
     end (loader.decode_stream): a worker thread gathers, uploads and plans sub-batch k+1 while the GPU decodes
-    sub-batch k, so the host work hides behind the device time."""
+    sub-batch k, so the host work hides behind the device time.
+
+    on_error="raise" (default): the first bad file raises, like the reference's constructor does for its one file.
+    on_error="return": nothing is raised for a bad file; its position in the result holds the exception instance
+    (NotJpeg / CorruptedJpeg / UnsupportedJpeg) instead of a decoder, and all other files are decoded."""
+    if on_error not in ("raise", "return"):
+        raise ValueError("on_error must be 'raise' or 'return'")
     files = list(files)
     if not files:
         return []
     chunk = BATCH_CHUNK if chunk is None else int(chunk)
     if chunk < 1:
         raise ValueError("chunk must be positive")
+    if on_error == "return":
+        return _decode_batch_tolerant(files, device, chunk)
     if len(files) > chunk + chunk // 2:
         from .loader import decode_stream
         out: List[JpegDecoder] = []
@@ -207,3 +215,31 @@ def decode_batch(files: Sequence[Union[str, Path, bytes]], device: Optional[Unio
     datas = [_read(f) for f in files]
     batch = decode_batch_on_device(datas, device=device)
     return [JpegDecoder(f, _batch=batch, _index=i) for i, f in enumerate(files)]
+
+
+def _decode_batch_tolerant(files: list, device, chunk: int) -> list:
+    """decode_batch(on_error="return"): header problems are found per file on the host (the same parser and plan
+    checks the batch path runs), entropy-data problems come back as the per-image device error words."""
+    from .errors import JpegError
+    from .pipeline import BatchPlan, error_for
+    results: list = [None] * len(files)
+    good: List[int] = []
+    datas = {}
+    for i, f in enumerate(files):
+        try:
+            d = _read(f)
+            BatchPlan([parse_jpeg(d)], [0], len(d))          # header, scan script and size checks of one file
+        except JpegError as e:
+            results[i] = e
+            continue
+        datas[i] = d
+        good.append(i)
+    for a in range(0, len(good), chunk):
+        idx = good[a:a + chunk]
+        batch = decode_batch_on_device([datas[i] for i in idx], device=device, check=False)
+        pipe = batch.stats["_pipe"]
+        err = pipe.err.cpu().numpy()                          # synchronises
+        for k, i in enumerate(idx):
+            e = error_for(err[k], i)
+            results[i] = e if e is not None else JpegDecoder(files[i], _batch=batch, _index=k)
+    return results

@@ -405,18 +405,23 @@ class DecodedBatch:
         return device_to_grids(p, buf)
 
 
-def raise_for_errors(err_words: np.ndarray) -> None:
-    """Map device error words to the reference's exception classes (jpeg_decoder.py:1714-1725)."""
-    bad = np.nonzero(err_words)[0]
-    if len(bad) == 0:
-        return
-    i = int(bad[0])
-    e = int(err_words[i])
+def error_for(word: int, i: int) -> Optional[Exception]:
+    """The exception a device error word stands for (None if the image decoded): jpeg_decoder.py:1714-1725."""
+    e = int(word)
+    if e == 0:
+        return None
     if e & _native.ERR_BAD_CODE:
-        raise CorruptedJpeg(f"Failed to decode image {i} (no Huffman code matches the data).")       # :718-719
+        return CorruptedJpeg(f"Failed to decode image {i} (no Huffman code matches the data).")       # :718-719
     if e & (_native.ERR_OVERRUN | _native.ERR_RST_COUNT | _native.ERR_COEF_INDEX):
-        raise CorruptedJpeg(f"Failed to decode image {i} (entropy-coded data ended early or is inconsistent).")
-    raise NativeLibraryError(f"image {i}: device decode error {e:#x}")
+        return CorruptedJpeg(f"Failed to decode image {i} (entropy-coded data ended early or is inconsistent).")
+    return NativeLibraryError(f"image {i}: device decode error {e:#x}")
+
+
+def raise_for_errors(err_words: np.ndarray) -> None:
+    """Map device error words to the reference's exception classes; raises for the first bad image."""
+    bad = np.nonzero(err_words)[0]
+    if len(bad):
+        raise error_for(err_words[int(bad[0])], int(bad[0]))
 
 
 class DevicePipeline:
@@ -425,6 +430,7 @@ class DevicePipeline:
     the file bytes, `launch` enqueues every kernel on the stream."""
 
     STAGES = ("unstuff", "plan", "spec", "fix", "write", "other_scans", "pixels")
+    EXTRA_PHASE_FLAGS = 0                   # OR-ed into `phases` of bj_entropy_decode; tests set BJ_PHASE_NO_BITMAP (8)
 
     def __init__(self, plan: BatchPlan, device=None, stream: Optional[torch.cuda.Stream] = None,
                  raw: Optional[torch.Tensor] = None, desc: Optional[Tuple[torch.Tensor, Dict[str, Tuple[int, int]]]] = None):
@@ -434,6 +440,7 @@ class DevicePipeline:
         self.plan = plan
         self.dev = require_cuda(device)
         self.L = _bind()
+        self.extra_phase_flags = self.EXTRA_PHASE_FLAGS
         g = plan.geom
         dev = self.dev
         with torch.cuda.device(dev):
@@ -529,6 +536,7 @@ class DevicePipeline:
                     break
 
                 def call(phases, grp=grp):
+                    phases |= self.extra_phase_flags
                     _native.check(L.bj_entropy_decode(
                         self.scans.data_ptr(), grp.first, grp.count, grp.mode, grp.max_sub, grp.max_streams,
                         grp.max_blocks, grp.max_lut, ctypes.byref(B), self.chain.data_ptr(), phases, cs),

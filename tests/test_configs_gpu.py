@@ -125,3 +125,14 @@ def test_multi_gpu_dispatcher_single_device():
     res = decode_files_multi_gpu(datas, devices=devs)
     for d, data in zip(res, datas):
         assert np.array_equal(d.image_tensor.cpu().numpy(), oracle.decode(data, want=("rgb",)).rgb)
+
+
+def test_chain_step_without_the_stream_head_bitmap(monkeypatch):
+    """Scans with more than 262144 subsequences do not fit the chain kernel's shared-memory bitmap of stream heads
+    and look the heads up by binary search instead; BJ_PHASE_NO_BITMAP forces that path on a file with thousands of
+    restart intervals (and on a progressive one), results unchanged."""
+    from pyjpegdecoder_b200.pipeline import DevicePipeline
+    monkeypatch.setattr(DevicePipeline, "EXTRA_PHASE_FLAGS", 8)
+    _check([_encode(3840, 2160, 1, subsampling=2, restart_marker_blocks=16),
+            _encode(1024, 768, 3, subsampling=2, progressive=True, restart_marker_rows=1),
+            _encode(640, 480, 4, subsampling=1)])

@@ -129,3 +129,41 @@ def test_output_consumers_dlpack_cuda_array_interface_and_save(tmp_path):
     assert np.array_equal(np.swapaxes(np.array(Image.open(p1)), 0, 1), z["rgb"])
     p3 = d.save(tmp_path / "out.unknownext")
     assert p3.suffix == ".png" and p3.exists()
+
+
+def test_on_error_return_reports_each_bad_file_and_decodes_the_rest():
+    """decode_batch(on_error="return"): bad files come back as exception instances in their positions (header
+    problems found on the host, entropy-data problems from the per-image device error words); good files of the
+    same batch are bit-exact."""
+    from pyjpegdecoder_b200 import CorruptedJpeg, JpegDecoder, JpegError, NotJpeg, decode_batch
+    from pyjpegdecoder_b200.parser import parse_jpeg
+    names = golden_case_names()[:6]
+    files, expect = [], []
+    for name in names:
+        data, z = _case(name)
+        files.append(data)
+        expect.append(z["rgb"])
+    files.insert(1, b"not a jpeg at all")
+    expect.insert(1, NotJpeg)
+    good, _ = _case(names[0])
+    files.insert(3, good[: len(good) // 2])                       # header intact, entropy data and EOI missing
+    expect.insert(3, JpegError)
+    p = parse_jpeg(good)
+    sc = p.scans[0]
+    broken = bytearray(good)
+    mid = (sc.data_start + sc.data_end) // 2
+    broken[mid:mid + 64] = bytes(64)                              # 512 zero bits: no such run of codes in this file
+    files.append(bytes(broken))
+    expect.append(None)                                           # decodes to something or is flagged, never raises
+    res = decode_batch(files, device="cuda:0", on_error="return")
+    assert len(res) == len(files)
+    for r, e in zip(res, expect):
+        if e is None:
+            assert isinstance(r, (JpegDecoder, CorruptedJpeg))
+        elif isinstance(e, type):
+            assert isinstance(r, e), r
+        else:
+            assert isinstance(r, JpegDecoder)
+            assert np.array_equal(r.image_array, e)
+    with pytest.raises(JpegError):
+        decode_batch(files, device="cuda:0")                      # the default still raises

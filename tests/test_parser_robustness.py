@@ -106,3 +106,14 @@ def test_rewritten_files_decode_to_the_same_pixels(name):
     for d in decode_batch(variants + variants, device="cuda:0"):      # 6 files: the fast planner path
         assert np.array_equal(d.image_array, z["rgb"])
     assert np.array_equal(decode_batch(variants[:1], device="cuda:0")[0].image_array, z["rgb"])
+
+
+def test_on_error_return_needs_no_device_for_files_that_fail_on_the_host():
+    """decode_batch(on_error="return") triages headers on the host: a list of files that are all bad comes back as
+    exception instances without touching the GPU (so this runs on the CPU box)."""
+    from pyjpegdecoder_b200 import JpegError, NotJpeg, decode_batch
+    res = decode_batch([b"", b"\x89PNG\r\n\x1a\n" + bytes(32), b"\xff\xd8\xff\xd9"], on_error="return")
+    assert len(res) == 3 and all(isinstance(r, JpegError) for r in res)
+    assert isinstance(res[1], NotJpeg)
+    with pytest.raises(ValueError):
+        decode_batch([b"x"], on_error="ignore")
