@@ -7,6 +7,8 @@ first chunk.  Two pinned staging buffers alternate; a chunk's buffer is reused o
 synchronised (its status words were read back).  No CPU decode path: the worker only prepares inputs."""
 from __future__ import annotations
 
+import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 from typing import Iterable, Iterator, List, Optional, Sequence, Union
@@ -21,20 +23,47 @@ from .stages import require_cuda
 Source = Union[str, Path, bytes, bytearray, memoryview]
 
 
-def _chunks(files: Iterable[Source], n: int) -> Iterator[List[Source]]:
+def _sizes(total: int, n: int) -> List[int]:
+    """Sub-batch sizes for `total` files, at most n each.  Short sub-batches at both ends: nothing runs on the GPU
+    before the first sub-batch has been gathered, uploaded and planned, and nothing overlaps the decode of the last
+    one once its upload is done (the pipeline is bound by the host->device link, so that decode is pure tail)."""
+    if n < 128 or total <= n + n // 2:
+        return [n] * (total // n) + ([total % n] if total % n else [])
+    head, tail = [n // 4, n // 2], [n // 2, n // 4]
+    sizes = list(head)
+    body = total - sum(head)
+    while body > sum(tail) + n:
+        sizes.append(n)
+        body -= n
+    return sizes + [body - sum(tail)] + tail
+
+
+def _chunks(files: Iterable[Source], n: int, ramp: bool = True) -> Iterator[List[Source]]:
+    """Cut the input into sub-batches of at most n files, in order.  With ramp=True the first two are smaller
+    (n/4, n/2) and, when the number of files is known, so are the last two (see _sizes)."""
+    sizes: List[int] = []
+    open_ended = True
+    if ramp and n >= 128:
+        if hasattr(files, "__len__"):
+            sizes, open_ended = _sizes(len(files), n), False
+        else:
+            sizes = [n // 4, n // 2]
     buf: List[Source] = []
     for f in files:
         buf.append(f)
-        if len(buf) == n:
+        if len(buf) == (sizes[0] if sizes else n):
             yield buf
             buf = []
+            if sizes:
+                sizes.pop(0)
     if buf:
         yield buf
+    assert open_ended or not sizes or sizes == [0]
 
 
 _N_SLOTS = 4
 _N_STREAMS = 3
-_WORKERS = 1
+_WORKERS = max(1, int(os.environ.get("BJ_STREAM_WORKERS", "1")))   # threads preparing sub-batches; 2 was slower and unstable (both gathers fight for host memory bandwidth, allocation order becomes random)
 
 
 _STREAM_POOL = {}
@@ -47,7 +76,8 @@ def _device_streams(dev: torch.device):
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     if key not in _STREAM_POOL:
         with torch.cuda.device(dev):
-            _STREAM_POOL[key] = (torch.cuda.Stream(dev), [torch.cuda.Stream(dev) for _ in range(_N_STREAMS)])
+            _STREAM_POOL[key] = (torch.cuda.Stream(dev), [torch.cuda.Stream(dev) for _ in range(_N_STREAMS)],
+                                 torch.cuda.Stream(dev))
     return _STREAM_POOL[key]
 
 
@@ -59,16 +89,25 @@ class _Uploader:
     def __init__(self, device):
         self.dev = require_cuda(device)
         self.stream = _device_streams(self.dev)[0]
-        self.inflight: List = []          # (copy-done event, pinned file buffer, pinned descriptor buffer)
+        # the (small) descriptor uploads have their own stream: behind the file bytes of the NEXT sub-batch, which the
+        # other worker may already have enqueued, they would hold their sub-batch back for a whole upload
+        self.desc_stream = _device_streams(self.dev)[2]
+        self.inflight: List = []          # (file-copy event, pinned file buffer, descriptor-copy event, pinned descriptor buffer)
         self.desc_free: List[torch.Tensor] = []
+        self.lock = threading.Lock()      # prepare() runs on _WORKERS threads
 
     def _reclaim(self, block: bool) -> None:
         from .pipeline import release_pinned
-        while self.inflight and (block and len(self.inflight) >= _N_SLOTS or self.inflight[0][0].query()):
-            ev, buf, dbuf = self.inflight.pop(0)
+        while True:
+            with self.lock:
+                if not self.inflight or not (block and len(self.inflight) >= _N_SLOTS or self.inflight[0][0].query()):
+                    return
+                ev, buf, dev_, dbuf = self.inflight.pop(0)
             ev.synchronize()
+            dev_.synchronize()
             release_pinned(buf)
-            self.desc_free.append(dbuf)
+            with self.lock:
+                self.desc_free.append(dbuf)
 
     def prepare(self, files: Sequence[Source], k: int, read_threads: int = 8):
         """Host side of chunk k: read, gather into a pinned buffer, start the H2D copy, plan, upload the descriptors."""
@@ -84,23 +123,28 @@ class _Uploader:
         with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
             raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=self.dev)
             raw_dev.copy_(raw_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
         if len(datas) >= FAST_PLAN_MIN_FILES:
             from .fastplan import plan_batch
             plan = plan_batch(raw_host, offsets, [len(d) for d in datas], walked=getattr(raw_host, "_bj_walk", None))
         else:
             plan = BatchPlan([parse_jpeg(d) for d in datas], offsets, raw_host.numel())
-        dbuf = self.desc_free.pop() if self.desc_free else None
-        desc_blob, layout, dbuf = upload_descriptors(plan, self.dev, self.stream, dbuf)
-        ev = torch.cuda.Event()
+        with self.lock:
+            dbuf = self.desc_free.pop() if self.desc_free else None
+        desc_blob, layout, dbuf = upload_descriptors(plan, self.dev, self.desc_stream, dbuf)
+        dev_ = torch.cuda.Event()
         with torch.cuda.device(self.dev):
-            ev.record(self.stream)
-        self.inflight.append((ev, raw_host, dbuf))
-        return list(files), packed, plan, raw_dev, ev, (desc_blob, layout)
+            dev_.record(self.desc_stream)
+        with self.lock:
+            self.inflight.append((ev, raw_host, dev_, dbuf))
+        return list(files), packed, plan, raw_dev, (ev, dev_), (desc_blob, layout)
 
     def close(self) -> None:
         from .pipeline import release_pinned
-        for ev, buf, _ in self.inflight:
+        for ev, buf, dev_, _ in self.inflight:
             ev.synchronize()
+            dev_.synchronize()
             release_pinned(buf)
         self.inflight = []
 
@@ -113,8 +157,8 @@ def _check(batch) -> None:
 
 def decode_stream(files: Iterable[Source], chunk: int = 512, device: Optional[Union[str, torch.device]] = None
                   ) -> Iterator[List[JpegDecoder]]:
-    """Decode an arbitrarily long sequence of files `chunk` at a time; yields one list of JpegDecoder objects
-    per chunk, in order.  Errors of a file (NotJpeg, CorruptedJpeg, ...) are raised when its chunk is reached.
+    """Decode an arbitrarily long sequence of files in sub-batches of at most `chunk` files (the first two are
+    smaller, see _chunks); yields one list of JpegDecoder objects per sub-batch, in order.  Errors of a file (NotJpeg, CorruptedJpeg, ...) are raised when its chunk is reached.
     Three things overlap: the worker thread prepares and uploads the chunks ahead, the GPU decodes up to three chunks
     on alternating streams (a chunk is checked only when two later ones have been enqueued), and the caller consumes
     the oldest finished chunk."""
@@ -150,12 +194,13 @@ def _stream(up, it, depth, device):
         refill()
         pending = []          # enqueued, not yet checked: up to _N_STREAMS - 1 chunks run ahead of the one being consumed
         while queue:
-            chunk_files, packed, plan, raw_dev, ev, desc = queue.pop(0).result()
+            chunk_files, packed, plan, raw_dev, (ev, ev_desc), desc = queue.pop(0).result()
             refill()
             st = streams[n_done % _N_STREAMS]
             n_done += 1
             raw_dev.record_stream(st)
             desc[0].record_stream(st)
+            st.wait_event(ev_desc)
             batch = decode_batch_on_device(None, device=device, packed=packed, plan=plan, check=False,
                                            raw_dev=raw_dev, raw_ready=ev, desc=desc, stream=st)
             pending.append((batch, chunk_files))

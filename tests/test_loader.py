@@ -18,6 +18,17 @@ def test_chunks_keeps_order_and_sizes():
     assert [len(c) for c in _chunks(range(10), 4)] == [4, 4, 2]
     assert [x for c in _chunks(iter(range(7)), 3) for x in c] == list(range(7))
     assert list(_chunks([], 5)) == []
+    # large sub-batches ramp up: n/4, n/2, then n (a short first sub-batch cuts the start-up latency)
+    assert [len(c) for c in _chunks(iter(range(2000)), 512)] == [128, 256, 512, 512, 512, 80]
+    assert [len(c) for c in _chunks(range(2000), 512, ramp=False)] == [512, 512, 512, 464]
+    # ... and down again when the length is known (the decode of the last sub-batch overlaps nothing)
+    assert [len(c) for c in _chunks(list(range(4096)), 512)] == [128, 256] + [512] * 6 + [256, 256, 128]
+    from pyjpegdecoder_b200.loader import _sizes
+    for total in (1, 127, 700, 769, 1000, 1153, 2000, 4096, 5000, 100000):
+        for n in (64, 128, 512, 1000):
+            sz = _sizes(total, n)
+            assert sum(sz) == total and all(0 < x <= n for x in sz), (total, n, sz)
+    assert [x for c in _chunks(iter(range(1000)), 256) for x in c] == list(range(1000))
 
 
 def test_decode_stream_needs_a_gpu_and_never_falls_back():

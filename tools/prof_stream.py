@@ -27,7 +27,8 @@ for rep in range(3):
         prev = None
         while queue:
             t0 = time.perf_counter()
-            chunk_files, packed, plan, raw_dev, ev, desc = queue.pop(0).result()
+            chunk_files, packed, plan, raw_dev, (ev, evd), desc = queue.pop(0).result()
+            torch.cuda.current_stream(up.dev).wait_event(evd)
             t1 = time.perf_counter(); T["wait"] += t1 - t0
             refill()
             raw_dev.record_stream(torch.cuda.current_stream(up.dev))
