@@ -186,7 +186,7 @@ BATCH_CHUNK = 512
 
 
 def decode_batch(files: Sequence[Union[str, Path, bytes]], device: Optional[Union[str, torch.device]] = None,
-                 chunk: Optional[int] = None, on_error: str = "raise") -> List[JpegDecoder]:
+                 chunk: Optional[int] = None, on_error: str = "raise", keep_coefficients: bool = False) -> List[JpegDecoder]:
     """Decode many files and return one JpegDecoder-like object per file (pixels stay on the device until
     `image_array` is read).  Small batches run as ONE device pipeline (one launch sequence for all files); batches
     larger than 1.5 x `chunk` files are cut into sub-batches of `chunk` files that flow through the streaming front
@@ -195,7 +195,11 @@ def decode_batch(files: Sequence[Union[str, Path, bytes]], device: Optional[Unio
 
     on_error="raise" (default): the first bad file raises, like the reference's constructor does for its one file.
     on_error="return": nothing is raised for a bad file; its position in the result holds the exception instance
-    (NotJpeg / CorruptedJpeg / UnsupportedJpeg) instead of a decoder, and all other files are decoded."""
+    (NotJpeg / CorruptedJpeg / UnsupportedJpeg) instead of a decoder, and all other files are decoded.
+
+    Large (sub-batched) calls keep only the pixels on the device: the coefficient planes -- as many bytes again -- are
+    released as each sub-batch completes unless keep_coefficients=True (`coefficient_planes()` then works on every
+    result, at twice the memory: 12.4 MB instead of 6.2 MB per 1080p image)."""
     if on_error not in ("raise", "return"):
         raise ValueError("on_error must be 'raise' or 'return'")
     files = list(files)
@@ -209,7 +213,7 @@ def decode_batch(files: Sequence[Union[str, Path, bytes]], device: Optional[Unio
     if len(files) > chunk + chunk // 2:
         from .loader import decode_stream
         out: List[JpegDecoder] = []
-        for part in decode_stream(files, chunk=chunk, device=device):
+        for part in decode_stream(files, chunk=chunk, device=device, keep_coefficients=keep_coefficients):
             out.extend(part)
         return out
     datas = [_read(f) for f in files]

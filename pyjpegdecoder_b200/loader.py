@@ -8,7 +8,6 @@ synchronised (its status words were read back).  No CPU decode path: the worker 
 from __future__ import annotations
 
 import os
-import threading
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 from typing import Iterable, Iterator, List, Optional, Sequence, Union
@@ -23,31 +22,23 @@ from .stages import require_cuda
 Source = Union[str, Path, bytes, bytearray, memoryview]
 
 
-def _sizes(total: int, n: int) -> List[int]:
-    """Sub-batch sizes for `total` files, at most n each.  Short sub-batches at both ends: nothing runs on the GPU
-    before the first sub-batch has been gathered, uploaded and planned, and nothing overlaps the decode of the last
-    one once its upload is done (the pipeline is bound by the host->device link, so that decode is pure tail)."""
-    if n < 128 or total <= n + n // 2:
-        return [n] * (total // n) + ([total % n] if total % n else [])
-    head, tail = [n // 4, n // 2], [n // 2, n // 4]
-    sizes = list(head)
-    body = total - sum(head)
-    while body > sum(tail) + n:
-        sizes.append(n)
-        body -= n
-    return sizes + [body - sum(tail)] + tail
+def _ramp(n: int) -> List[int]:
+    """Sizes of the first sub-batches when the full size is n: n/2, then growing by a quarter per step.  Nothing can
+    run on the GPU until the first sub-batch has been gathered, uploaded and planned, so a shorter one cuts the
+    start-up latency; the host prepares files ~1.4x faster than the GPU decodes them, so growing faster than that
+    would leave the GPU waiting for the second and third sub-batch instead."""
+    if n < 128 or os.environ.get("BJ_STREAM_RAMP", "1") == "0":
+        return []
+    out, c = [], n // 2
+    while c < n:
+        out.append(c)
+        c += max(1, c // 4)
+    return out
 
 
 def _chunks(files: Iterable[Source], n: int, ramp: bool = True) -> Iterator[List[Source]]:
-    """Cut the input into sub-batches of at most n files, in order.  With ramp=True the first two are smaller
-    (n/4, n/2) and, when the number of files is known, so are the last two (see _sizes)."""
-    sizes: List[int] = []
-    open_ended = True
-    if ramp and n >= 128:
-        if hasattr(files, "__len__"):
-            sizes, open_ended = _sizes(len(files), n), False
-        else:
-            sizes = [n // 4, n // 2]
+    """Cut the input into sub-batches of at most n files, in order; with ramp=True the first ones are smaller."""
+    sizes = _ramp(n) if ramp else []
     buf: List[Source] = []
     for f in files:
         buf.append(f)
@@ -58,12 +49,10 @@ def _chunks(files: Iterable[Source], n: int, ramp: bool = True) -> Iterator[List
                 sizes.pop(0)
     if buf:
         yield buf
-    assert open_ended or not sizes or sizes == [0]
 
 
-_N_SLOTS = 4
-_N_STREAMS = 3
-_WORKERS = max(1, int(os.environ.get("BJ_STREAM_WORKERS", "1")))   # threads preparing sub-batches; 2 was slower and unstable (both gathers fight for host memory bandwidth, allocation order becomes random)
+_N_STREAMS = max(2, int(os.environ.get("BJ_STREAM_DEPTH", "3")))   # sub-batches in flight on the GPU, each on its own stream
+_N_SLOTS = _N_STREAMS + 1
 
 
 _STREAM_POOL = {}
@@ -92,26 +81,28 @@ class _Uploader:
         # the (small) descriptor uploads have their own stream: behind the file bytes of the NEXT sub-batch, which the
         # other worker may already have enqueued, they would hold their sub-batch back for a whole upload
         self.desc_stream = _device_streams(self.dev)[2]
-        self.inflight: List = []          # (file-copy event, pinned file buffer, descriptor-copy event, pinned descriptor buffer)
+        # pack_stage and plan_stage each own their lists (they may run on different threads)
+        self.inflight: List = []          # pack_stage: (file-copy event, pinned file buffer)
+        self.inflight_desc: List = []     # plan_stage: (descriptor-copy event, pinned descriptor buffer)
         self.desc_free: List[torch.Tensor] = []
-        self.lock = threading.Lock()      # prepare() runs on _WORKERS threads
 
     def _reclaim(self, block: bool) -> None:
+        """Give pinned file buffers whose upload has completed back to the pool; with block=True wait for the oldest
+        upload while _N_SLOTS buffers are out (called by pack_stage only)."""
         from .pipeline import release_pinned
-        while True:
-            with self.lock:
-                if not self.inflight or not (block and len(self.inflight) >= _N_SLOTS or self.inflight[0][0].query()):
-                    return
-                ev, buf, dev_, dbuf = self.inflight.pop(0)
+        while self.inflight and (block and len(self.inflight) >= _N_SLOTS or self.inflight[0][0].query()):
+            ev, buf = self.inflight.pop(0)
             ev.synchronize()
-            dev_.synchronize()
             release_pinned(buf)
-            with self.lock:
-                self.desc_free.append(dbuf)
 
-    def prepare(self, files: Sequence[Source], k: int, read_threads: int = 8):
-        """Host side of chunk k: read, gather into a pinned buffer, start the H2D copy, plan, upload the descriptors."""
-        from .pipeline import upload_descriptors
+    def _reclaim_desc(self) -> None:
+        """Pinned descriptor staging buffers whose upload has completed (called by plan_stage only)."""
+        while self.inflight_desc and self.inflight_desc[0][0].query():
+            self.desc_free.append(self.inflight_desc.pop(0)[1])
+
+    def pack_stage(self, files: Sequence[Source], read_threads: int = 8):
+        """First half of the host side of a sub-batch (C code, releases the GIL): read, gather into a pinned buffer,
+        start the H2D copy of the file bytes."""
         if any(not isinstance(f, (bytes, bytearray, memoryview)) for f in files) and len(files) > 1:
             with ThreadPoolExecutor(min(read_threads, len(files))) as ex:
                 datas = list(ex.map(_read, files))
@@ -119,34 +110,49 @@ class _Uploader:
             datas = [_read(f) for f in files]
         self._reclaim(block=True)
         packed = pack_files(datas, pin=True, reuse_slot="checkout", walk=len(datas) >= FAST_PLAN_MIN_FILES)
-        raw_host, offsets = packed
+        raw_host = packed[0]
         with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
             raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=self.dev)
             raw_dev.copy_(raw_host, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self.inflight.append((ev, raw_host))
+        return list(files), datas, packed, raw_dev, ev
+
+    def plan_stage(self, packed_stage):
+        """Second half (numpy / Python, holds the GIL): plan the sub-batch and upload its descriptors.  Runs on its own
+        thread so that it overlaps the gather of the next sub-batch.  packed_stage: pack_stage's result or its future."""
+        from .pipeline import upload_descriptors
+        if hasattr(packed_stage, "result"):
+            packed_stage = packed_stage.result()
+        files, datas, packed, raw_dev, ev = packed_stage
+        raw_host, offsets = packed
         if len(datas) >= FAST_PLAN_MIN_FILES:
             from .fastplan import plan_batch
             plan = plan_batch(raw_host, offsets, [len(d) for d in datas], walked=getattr(raw_host, "_bj_walk", None))
         else:
             plan = BatchPlan([parse_jpeg(d) for d in datas], offsets, raw_host.numel())
-        with self.lock:
-            dbuf = self.desc_free.pop() if self.desc_free else None
+        self._reclaim_desc()
+        dbuf = self.desc_free.pop() if self.desc_free else None
         desc_blob, layout, dbuf = upload_descriptors(plan, self.dev, self.desc_stream, dbuf)
         dev_ = torch.cuda.Event()
         with torch.cuda.device(self.dev):
             dev_.record(self.desc_stream)
-        with self.lock:
-            self.inflight.append((ev, raw_host, dev_, dbuf))
-        return list(files), packed, plan, raw_dev, (ev, dev_), (desc_blob, layout)
+        self.inflight_desc.append((dev_, dbuf))
+        return files, packed, plan, raw_dev, (ev, dev_), (desc_blob, layout)
+
+    def prepare(self, files: Sequence[Source], k: int = 0, read_threads: int = 8):
+        """Host side of one sub-batch, both halves on the calling thread."""
+        return self.plan_stage(self.pack_stage(files, read_threads))
 
     def close(self) -> None:
         from .pipeline import release_pinned
-        for ev, buf, dev_, _ in self.inflight:
+        for ev, buf in self.inflight:
             ev.synchronize()
-            dev_.synchronize()
             release_pinned(buf)
-        self.inflight = []
+        for ev, _ in self.inflight_desc:
+            ev.synchronize()
+        self.inflight, self.inflight_desc = [], []
 
 
 def _check(batch) -> None:
@@ -155,8 +161,8 @@ def _check(batch) -> None:
     raise_for_errors(pipe.err.cpu().numpy())
 
 
-def decode_stream(files: Iterable[Source], chunk: int = 512, device: Optional[Union[str, torch.device]] = None
-                  ) -> Iterator[List[JpegDecoder]]:
+def decode_stream(files: Iterable[Source], chunk: int = 512, device: Optional[Union[str, torch.device]] = None,
+                  keep_coefficients: bool = False) -> Iterator[List[JpegDecoder]]:
     """Decode an arbitrarily long sequence of files in sub-batches of at most `chunk` files (the first two are
     smaller, see _chunks); yields one list of JpegDecoder objects per sub-batch, in order.  Errors of a file (NotJpeg, CorruptedJpeg, ...) are raised when its chunk is reached.
     Three things overlap: the worker thread prepares and uploads the chunks ahead, the GPU decodes up to three chunks
@@ -168,28 +174,28 @@ def decode_stream(files: Iterable[Source], chunk: int = 512, device: Optional[Un
     it = _chunks(files, chunk)
     depth = _N_SLOTS - 1                     # chunks prepared ahead of the one being enqueued
     try:
-        yield from _stream(up, it, depth, device)
+        yield from _stream(up, it, depth, device, keep_coefficients)
     finally:
         up.close()
 
 
-def _stream(up, it, depth, device):
+def _stream(up, it, depth, device, keep_coefficients=False):
     # consecutive chunks run on alternating streams: the latency-bound tail of chunk k (a few long-running CTAs, the
     # one-CTA-per-scan prefix kernel) overlaps the start of chunk k+1 instead of leaving the GPU half empty
     streams = _device_streams(up.dev)[1]
     n_done = 0
-    with ThreadPoolExecutor(_WORKERS) as worker:
+    # ONE worker thread prepares the sub-batches.  Two were tried, both as two whole-task workers and as a gather
+    # thread feeding a planning thread: the gathers fight for host memory bandwidth, the Python halves for the GIL, and
+    # the run-to-run spread (61..73 ms per 4096 files) ate the 1-2 ms the overlap gained.
+    with ThreadPoolExecutor(1) as worker:
         queue = []
-        k = 0
 
         def refill():
-            nonlocal k
             while len(queue) < depth:
                 nxt = next(it, None)
                 if nxt is None:
                     return
-                queue.append(worker.submit(up.prepare, nxt, k))
-                k += 1
+                queue.append(worker.submit(up.prepare, nxt))
 
         refill()
         pending = []          # enqueued, not yet checked: up to _N_STREAMS - 1 chunks run ahead of the one being consumed
@@ -207,8 +213,10 @@ def _stream(up, it, depth, device):
             if len(pending) >= _N_STREAMS:
                 b, fl = pending.pop(0)
                 _check(b)
+                b.release_work_buffers(keep_coefficients)
                 yield [JpegDecoder(f, _batch=b, _index=i) for i, f in enumerate(fl)]
         while pending:
             b, fl = pending.pop(0)
             _check(b)
+            b.release_work_buffers(keep_coefficients)
             yield [JpegDecoder(f, _batch=b, _index=i) for i, f in enumerate(fl)]

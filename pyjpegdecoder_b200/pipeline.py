@@ -232,7 +232,14 @@ _PINNED_FREE: List[torch.Tensor] = []             # checkout / release list shar
 _PINNED_LOCK = threading.Lock()
 
 
+_PINNED_LARGEST = 0
+
+
 def _pinned_take(total: int) -> torch.Tensor:
+    """A pinned buffer of at least `total` bytes from the free list, else a new one.  New buffers are never smaller
+    than the largest one handed out so far: pinning costs ~0.7 ms per MB, and with sub-batches of several sizes a
+    free list of mixed sizes would keep running out of buffers that fit the large ones."""
+    global _PINNED_LARGEST
     with _PINNED_LOCK:
         best = None
         for i, t in enumerate(_PINNED_FREE):
@@ -240,7 +247,9 @@ def _pinned_take(total: int) -> torch.Tensor:
                 best = i
         if best is not None:
             return _PINNED_FREE.pop(best)
-    return torch.empty(max(total, 1 << 20) * 5 // 4, dtype=torch.uint8, pin_memory=True)
+        size = max(max(total, 1 << 20) * 5 // 4, _PINNED_LARGEST)
+        _PINNED_LARGEST = size
+    return torch.empty(size, dtype=torch.uint8, pin_memory=True)
 
 
 def release_pinned(buf: torch.Tensor) -> None:
@@ -397,8 +406,27 @@ class DecodedBatch:
         """The reference's layout: (W, H, 3) or (W, H) view (jpeg_decoder.py:626, :1373-1386)."""
         return self.images[i].transpose(0, 1)
 
+    def release_work_buffers(self, keep_coefficients: bool = False) -> None:
+        """Drop everything but the pixels: the pipeline object with the un-stuffed bitstream, the decoder states and
+        (unless asked to keep them) the coefficient planes -- as much memory again as the RGB output.  Safe right
+        after the launches: the buffers were allocated on the stream the kernels run on, so the caching allocator
+        hands them to later work of that stream only."""
+        pipe = self.stats.pop("_pipe", None)
+        if pipe is not None:
+            coef = pipe.coef
+            for name in ("raw", "words", "tile_sum", "stream_start", "stream_end", "stream_sub", "sub_entry", "sub_exit",
+                         "sub_count", "sub_prefix", "chain", "coef", "blk_pos", "B"):
+                setattr(pipe, name, None)
+            if keep_coefficients:
+                self.coef = coef
+        if not keep_coefficients:
+            self.coef = None
+
     def coefficient_grids(self, i: int) -> List[np.ndarray]:
         from .layout import device_to_grids, total_blocks
+        if self.coef is None:
+            raise RuntimeError("the coefficient planes of this sub-batch were released after decoding; "
+                               "use decode_batch(..., keep_coefficients=True) or decode_stream(..., keep_coefficients=True)")
         p = self.plan.parsed[i]
         b0 = self.plan.geom.block_offsets[i]
         buf = self.coef[b0:b0 + total_blocks(p)].cpu().numpy()

@@ -18,16 +18,9 @@ def test_chunks_keeps_order_and_sizes():
     assert [len(c) for c in _chunks(range(10), 4)] == [4, 4, 2]
     assert [x for c in _chunks(iter(range(7)), 3) for x in c] == list(range(7))
     assert list(_chunks([], 5)) == []
-    # large sub-batches ramp up: n/4, n/2, then n (a short first sub-batch cuts the start-up latency)
-    assert [len(c) for c in _chunks(iter(range(2000)), 512)] == [128, 256, 512, 512, 512, 80]
+    # large sub-batches ramp up from n/2 by a quarter per step (a short first sub-batch cuts the start-up latency)
+    assert [len(c) for c in _chunks(iter(range(3000)), 512)] == [256, 320, 400, 500, 512, 512, 500]
     assert [len(c) for c in _chunks(range(2000), 512, ramp=False)] == [512, 512, 512, 464]
-    # ... and down again when the length is known (the decode of the last sub-batch overlaps nothing)
-    assert [len(c) for c in _chunks(list(range(4096)), 512)] == [128, 256] + [512] * 6 + [256, 256, 128]
-    from pyjpegdecoder_b200.loader import _sizes
-    for total in (1, 127, 700, 769, 1000, 1153, 2000, 4096, 5000, 100000):
-        for n in (64, 128, 512, 1000):
-            sz = _sizes(total, n)
-            assert sum(sz) == total and all(0 < x <= n for x in sz), (total, n, sz)
     assert [x for c in _chunks(iter(range(1000)), 256) for x in c] == list(range(1000))
 
 
@@ -132,3 +125,22 @@ def test_lazy_views_and_lazy_decoder_attributes_on_cpu():
     assert d.image_array.shape == (17, 33, 3)           # the reference's x-major layout
     with pytest.raises(AttributeError):
         d.no_such_attribute
+
+
+@pytest.mark.gpu
+def test_streamed_sub_batches_release_their_work_buffers():
+    """decode_stream keeps only the pixels of a finished sub-batch (the coefficient planes are as large again);
+    keep_coefficients=True keeps the planes readable."""
+    from pyjpegdecoder_b200 import decode_batch, decode_stream
+    files = [_jpeg(64, 48, i) for i in range(12)]
+    ref = decode_batch(files, device="cuda:0")
+    got = [d for part in decode_stream(files, chunk=5, device="cuda:0") for d in part]
+    assert got[0]._batch.coef is None and "_pipe" not in got[0]._batch.stats
+    for a, b in zip(got, ref):
+        assert np.array_equal(a.image_array, b.image_array)
+    with pytest.raises(RuntimeError):
+        got[0].coefficient_planes()
+    kept = [d for part in decode_stream(files, chunk=5, device="cuda:0", keep_coefficients=True) for d in part]
+    for a, b in zip(kept, ref):
+        for pa, pb in zip(a.coefficient_planes(), b.coefficient_planes()):
+            assert np.array_equal(pa, pb)

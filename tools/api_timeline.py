@@ -28,7 +28,8 @@ def main():
             return r
         setattr(obj, name, inner)
 
-    wrap(loader._Uploader, "prepare", "prepare")
+    wrap(loader._Uploader, "pack_stage", "pack")
+    wrap(loader._Uploader, "plan_stage", "plan")
     gpu = []
     real_dbod = loader.decode_batch_on_device
 
@@ -43,11 +44,8 @@ def main():
     loader.decode_batch_on_device = dbod
     wrap(loader, "decode_batch_on_device", "enqueue")
     wrap(loader, "_check", "check")
-    wrap(loader, "pack_files", "  pack")
-    from pyjpegdecoder_b200 import fastplan
-    wrap(fastplan, "plan_batch", "  plan")
-    wrap(pipeline, "upload_descriptors", "  desc")
-    for rep in range(3):
+    runs = []
+    for rep in range(int(sys.argv[3]) if len(sys.argv) > 3 else 3):
         log.clear()
         gpu.clear()
         t0 = time.perf_counter()
@@ -56,15 +54,15 @@ def main():
         t1 = time.perf_counter()
         del res
         print(f"rep {rep}: {1e3 * (t1 - t0):.1f} ms")
-    for tag, a, b in sorted(log, key=lambda x: x[1]):
-        if tag.startswith("  "):
-            continue
-        print(f"{tag:10s} {1e3 * (a - t0):7.2f} -> {1e3 * (b - t0):7.2f}  ({1e3 * (b - a):5.2f} ms)")
-
-
-    base = gpu[0][0]
-    for e0, e1, nimg in gpu:
-        print(f"gpu sub-batch: start {base.elapsed_time(e0):7.2f}  end {base.elapsed_time(e1):7.2f}  ({e0.elapsed_time(e1):5.2f} ms)")
+        if rep:
+            runs.append((t1 - t0, t0, list(log), [(a, b) for a, b, _ in gpu]))
+    for title, (dt, t0, lg, gp) in (("slowest", max(runs, key=lambda r: r[0])), ("fastest", min(runs, key=lambda r: r[0]))):
+        print(f"--- {title}: {1e3 * dt:.1f} ms")
+        for tag, a, b in sorted(lg, key=lambda x: x[1]):
+            print(f"{tag:10s} {1e3 * (a - t0):7.2f} -> {1e3 * (b - t0):7.2f}  ({1e3 * (b - a):5.2f} ms)")
+        base = gp[0][0]
+        for e0, e1 in gp:
+            print(f"gpu sub-batch: start {base.elapsed_time(e0):7.2f}  end {base.elapsed_time(e1):7.2f}  ({e0.elapsed_time(e1):5.2f} ms)")
 
 
 if __name__ == "__main__":
