@@ -145,7 +145,7 @@ typedef struct bj_scan {
  *   sub_prefix   exclusive prefix sums of sub_count (in subsequence order)
  */
 typedef struct bj_entropy_buffers {
-    const uint32_t* words;
+    const uint32_t* words;  /* 16-byte aligned (write_kernel copies it in 16-byte groups) */
     uint64_t words_len;     /* in 32-bit words, including 64 words of slack at the end */
     uint64_t* stream_start;
     uint64_t* stream_end;
