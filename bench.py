@@ -450,6 +450,36 @@ def main():
                       "what": f"ONE batch of {n_img} files split across {world} rank(s)"},
            "host_threads_per_rank": int(os.environ.get("BJ_HOST_THREADS", "0")) or None}
 
+    # ---- the reference's actual return type at batch scale: numpy arrays in HOST memory.  decode_batch(to_host=True)
+    #      sends the pixels of every sub-batch back in one pinned transfer behind the decode of the next ones; the
+    #      figure is bound by PCIe (3 bytes per pixel out against ~0.19 in).  N = 1 only, 1024 files (6.4 GB of
+    #      pinned host memory). ------------------------------------------------------------------------------------
+    host_px = None
+    if world == 1 and n_img >= 1024 and not args.no_configs:
+        n_host = 1024
+
+        def host_once():
+            res = decode_batch(datas_api[:n_host], device=dev, to_host=True)
+            checksum = 0
+            for d in res:
+                a = d.image_array                      # (W, H, 3) numpy view of the pinned copy; waits for its transfer
+                checksum += int(a[0, 0, 0])
+            return checksum
+        for _ in range(2):
+            host_once()
+        ts = []
+        for _ in range(3):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            host_once()
+            ts.append(time.perf_counter() - t0)
+        dt = float(np.median(ts))
+        host_px = {"value": n_host * W * H / 1e6 / dt, "unit": "MP/s", "images": n_host, "ms": dt * 1e3,
+                   "d2h_gbs": n_host * W * H * 3 / dt / 1e9,
+                   "what": "decode_batch(list of bytes, to_host=True) and image_array of every result: pixels as numpy arrays "
+                           "in (pinned) host memory, like the reference returns them; one device->host transfer per "
+                           "sub-batch, overlapped with the decode of the following ones; median of 3"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -529,7 +559,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline, "roofline_pixels": roofline_pixels, "stages": stages,
         "bitstream_gbs": {k: scan_bytes / (stage_ms[k] * 1e-3) / 1e9 for k in ("unstuff", "spec", "write") if k in stage_ms},
-        "cpu_baseline": cpu, "cpu_baseline_python": cpu_python, "public_api_e2e": api, "configs": configs,
+        "cpu_baseline": cpu, "cpu_baseline_python": cpu_python, "public_api_e2e": api, "host_pixels_e2e": host_px, "configs": configs,
         "device_bytes": device_bytes, "gen_seconds": t_gen,
     }
     print(json.dumps(line), flush=True)

@@ -66,7 +66,7 @@ def _device_streams(dev: torch.device):
     if key not in _STREAM_POOL:
         with torch.cuda.device(dev):
             _STREAM_POOL[key] = (torch.cuda.Stream(dev), [torch.cuda.Stream(dev) for _ in range(_N_STREAMS)],
-                                 torch.cuda.Stream(dev))
+                                 torch.cuda.Stream(dev), torch.cuda.Stream(dev))
     return _STREAM_POOL[key]
 
 
@@ -162,7 +162,7 @@ def _check(batch) -> None:
 
 
 def decode_stream(files: Iterable[Source], chunk: int = 512, device: Optional[Union[str, torch.device]] = None,
-                  keep_coefficients: bool = False) -> Iterator[List[JpegDecoder]]:
+                  keep_coefficients: bool = False, to_host: bool = False) -> Iterator[List[JpegDecoder]]:
     """Decode an arbitrarily long sequence of files in sub-batches of at most `chunk` files (the first two are
     smaller, see _chunks); yields one list of JpegDecoder objects per sub-batch, in order.  Errors of a file (NotJpeg, CorruptedJpeg, ...) are raised when its chunk is reached.
     Three things overlap: the worker thread prepares and uploads the chunks ahead, the GPU decodes up to three chunks
@@ -174,15 +174,16 @@ def decode_stream(files: Iterable[Source], chunk: int = 512, device: Optional[Un
     it = _chunks(files, chunk)
     depth = _N_SLOTS - 1                     # chunks prepared ahead of the one being enqueued
     try:
-        yield from _stream(up, it, depth, device, keep_coefficients)
+        yield from _stream(up, it, depth, device, keep_coefficients, to_host)
     finally:
         up.close()
 
 
-def _stream(up, it, depth, device, keep_coefficients=False):
+def _stream(up, it, depth, device, keep_coefficients=False, to_host=False):
     # consecutive chunks run on alternating streams: the latency-bound tail of chunk k (a few long-running CTAs, the
     # one-CTA-per-scan prefix kernel) overlaps the start of chunk k+1 instead of leaving the GPU half empty
     streams = _device_streams(up.dev)[1]
+    d2h = _device_streams(up.dev)[3]          # to_host=True: the pixels of finished sub-batches go back on their own stream
     n_done = 0
     # ONE worker thread prepares the sub-batches.  Two were tried, both as two whole-task workers and as a gather
     # thread feeding a planning thread: the gathers fight for host memory bandwidth, the Python halves for the GIL, and
@@ -214,9 +215,13 @@ def _stream(up, it, depth, device, keep_coefficients=False):
                 b, fl = pending.pop(0)
                 _check(b)
                 b.release_work_buffers(keep_coefficients)
+                if to_host:
+                    b.start_host_copy(d2h, None)
                 yield [JpegDecoder(f, _batch=b, _index=i) for i, f in enumerate(fl)]
         while pending:
             b, fl = pending.pop(0)
             _check(b)
             b.release_work_buffers(keep_coefficients)
+            if to_host:
+                b.start_host_copy(d2h, None)
             yield [JpegDecoder(f, _batch=b, _index=i) for i, f in enumerate(fl)]

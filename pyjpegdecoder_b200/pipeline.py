@@ -406,6 +406,39 @@ class DecodedBatch:
         """The reference's layout: (W, H, 3) or (W, H) view (jpeg_decoder.py:626, :1373-1386)."""
         return self.images[i].transpose(0, 1)
 
+    def start_host_copy(self, copy_stream: Optional[torch.cuda.Stream] = None, after: Optional[torch.cuda.Stream] = None) -> None:
+        """Begin ONE device->host copy of all pixels of the batch into pinned memory (on `copy_stream`, after the work
+        enqueued on `after` so far).  `host_image(i)` then hands out numpy views of that buffer: what the reference
+        returns (`image_array`, host memory) at batch scale costs one large PCIe transfer instead of a pageable copy
+        per image."""
+        if getattr(self, "_host", None) is not None:
+            return
+        dev = self.out.device
+        with torch.cuda.device(dev):
+            cs = copy_stream if copy_stream is not None else torch.cuda.current_stream(dev)
+            src = after if after is not None else torch.cuda.current_stream(dev)
+            if cs is not src:
+                ev = torch.cuda.Event()
+                ev.record(src)
+                cs.wait_event(ev)
+            host = torch.empty(self.out.numel(), dtype=self.out.dtype, pin_memory=True)
+            with torch.cuda.stream(cs):
+                host.copy_(self.out, non_blocking=True)
+                self.out.record_stream(cs)
+                done = torch.cuda.Event()
+                done.record(cs)
+        self._host, self._host_done = host, done
+        self._host_views = _LazyViews(self.plan.geom, host)
+
+    def host_image(self, i: int) -> Optional[np.ndarray]:
+        """(H, W, 3) / (H, W) numpy view of image i in the pinned host copy (None if start_host_copy was not called)."""
+        if getattr(self, "_host", None) is None:
+            return None
+        if self._host_done is not None:
+            self._host_done.synchronize()
+            self._host_done = None
+        return self._host_views[i].numpy()
+
     def release_work_buffers(self, keep_coefficients: bool = False) -> None:
         """Drop everything but the pixels: the pipeline object with the un-stuffed bitstream, the decoder states and
         (unless asked to keep them) the coefficient planes -- as much memory again as the RGB output.  Safe right

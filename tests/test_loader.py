@@ -144,3 +144,18 @@ def test_streamed_sub_batches_release_their_work_buffers():
     for a, b in zip(kept, ref):
         for pa, pb in zip(a.coefficient_planes(), b.coefficient_planes()):
             assert np.array_equal(pa, pb)
+
+
+@pytest.mark.gpu
+def test_to_host_gives_the_same_arrays_through_one_copy_per_sub_batch():
+    """to_host=True: image_array is a view of the sub-batch's pinned host copy (the reference's return type, host
+    memory) -- same values and layout as the per-image path, for the one-shot and the streamed call."""
+    from pyjpegdecoder_b200 import decode_batch, decode_stream
+    files = [_jpeg(40 + 8 * (i % 5), 32 + 8 * (i % 3), i, subsampling=2 if i % 2 else 0) for i in range(14)]
+    ref = decode_batch(files, device="cuda:0")
+    one = decode_batch(files, device="cuda:0", to_host=True)
+    many = [d for part in decode_stream(files, chunk=4, device="cuda:0", to_host=True) for d in part]
+    for r, a, b in zip(ref, one, many):
+        assert a._batch.host_image(a._index) is not None and b._batch.host_image(b._index) is not None
+        assert a.image_array.shape == r.image_array.shape == b.image_array.shape
+        assert np.array_equal(a.image_array, r.image_array) and np.array_equal(b.image_array, r.image_array)
