@@ -450,6 +450,28 @@ def main():
                       "what": f"ONE batch of {n_img} files split across {world} rank(s)"},
            "host_threads_per_rank": int(os.environ.get("BJ_HOST_THREADS", "0")) or None}
 
+    # ---- the same public call on PATHS (the reference's entry point takes a Path): the distinct files are written
+    #      to a temporary directory once (they stay in the page cache), the list of n_img paths cycles through them;
+    #      file reads go straight into the pinned staging buffer.  N = 1 only. ------------------------------------
+    api_paths = None
+    if world == 1 and not args.no_configs:
+        import shutil
+        import tempfile
+        tmpdir = Path(tempfile.mkdtemp(prefix="bj_bench_"))
+        try:
+            fpaths = []
+            for i, fdata in enumerate(files):
+                fp = tmpdir / f"img{i:04d}.jpg"
+                fp.write_bytes(fdata)
+                fpaths.append(fp)
+            paths_api = [fpaths[i % len(fpaths)] for i in range(n_img)]
+            dt_paths = api_time(paths_api)
+            api_paths = {"value": n_img * W * H / 1e6 / dt_paths, "unit": "MP/s", "images": n_img, "ms": dt_paths * 1e3,
+                         "what": "decode_batch(list of pathlib.Path), files in the page cache: read straight into pinned memory, "
+                                 "marker walk + plan, H2D, all kernels, status read-back; median of 3"}
+        finally:
+            shutil.rmtree(tmpdir, ignore_errors=True)
+
     # ---- the reference's actual return type at batch scale: numpy arrays in HOST memory.  decode_batch(to_host=True)
     #      sends the pixels of every sub-batch back in one pinned transfer behind the decode of the next ones; the
     #      figure is bound by PCIe (3 bytes per pixel out against ~0.19 in).  N = 1 only, 1024 files (6.4 GB of
@@ -559,7 +581,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline, "roofline_pixels": roofline_pixels, "stages": stages,
         "bitstream_gbs": {k: scan_bytes / (stage_ms[k] * 1e-3) / 1e9 for k in ("unstuff", "spec", "write") if k in stage_ms},
-        "cpu_baseline": cpu, "cpu_baseline_python": cpu_python, "public_api_e2e": api, "host_pixels_e2e": host_px, "configs": configs,
+        "cpu_baseline": cpu, "cpu_baseline_python": cpu_python, "public_api_e2e": api, "public_api_paths_e2e": api_paths, "host_pixels_e2e": host_px, "configs": configs,
         "device_bytes": device_bytes, "gen_seconds": t_gen,
     }
     print(json.dumps(line), flush=True)

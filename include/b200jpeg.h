@@ -269,6 +269,17 @@ void bj_host_pack(const uint8_t* const* src, const uint64_t* size, const uint64_
 void bj_host_pack_walk_keys(const uint8_t* const* src, const uint64_t* size, const uint64_t* off, int n_files, uint8_t* dst,
                             bj_host_entry* entries, int max_entries, int32_t* counts, uint64_t* key_hash, int n_threads);
 
+/* File sizes from host threads: size[i] = bytes of paths[i], or -errno. */
+void bj_host_stat_files(const char* const* paths, int n_files, int64_t* size, int n_threads);
+
+/* Read n_files files straight into a packed buffer (dst + off[i], size[i] bytes as measured by bj_host_stat_files)
+ * from host threads; with entries != NULL every file is also walked and hashed like bj_host_walk_batch_keys right
+ * after it was read.  status[i] = 0 or the errno of the failed open / read.  This is the file-read step in front of
+ * the reference's JpegDecoder(Path) (jpeg_decoder.py:32-33) for a whole batch, without intermediate copies. */
+void bj_host_read_files(const char* const* paths, const uint64_t* size, const uint64_t* off, int n_files, uint8_t* dst,
+                        int32_t* status, bj_host_entry* entries, int max_entries, int32_t* counts, uint64_t* key_hash,
+                        int n_threads);
+
 /*
  * Pixel stages.  Replaces, for a whole batch of images in one launch:
  *   undo_zigzag * Q              jpeg_decoder.py:1648-1662, :869, :1347-1348   (int16 product wraps)

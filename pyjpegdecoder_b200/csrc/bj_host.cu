@@ -53,6 +53,11 @@ uint32_t bj_host_count_sos(const uint8_t* data, uint64_t n, uint64_t pos) {
 // in Python (parser.py).  Entries: marker 0x100 = entropy-coded run [start, end); otherwise a marker
 // segment whose payload is [start, end) (start points after the 2-byte length).  Returns the number of
 // entries, or -1 if the file does not start with FFD8FF, or -2 if max_entries is too small.
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <thread>
 #include <vector>
 
@@ -257,3 +262,77 @@ extern "C" void bj_host_pack_walk_keys(const uint8_t* const* src, const uint64_t
     for (auto& x : th) x.join();
 }
 
+
+
+// ---- files straight from disk (page cache) into the packed buffer ----------------------------------------
+// Python-level open/read/close costs ~45 us per file even from 16 threads (the interpreter lock); these run the same
+// system calls from plain host threads.
+
+// size[i] = size of paths[i] in bytes, or -errno.
+extern "C" void bj_host_stat_files(const char* const* paths, int n_files, int64_t* size, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_files) n_threads = n_files > 0 ? n_files : 1;
+    auto work = [&](int t) {
+        for (int i = t; i < n_files; i += n_threads) {
+            struct stat st;
+            size[i] = (stat(paths[i], &st) == 0) ? (int64_t)st.st_size : -(int64_t)errno;
+        }
+    };
+    if (n_threads == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+}
+
+static int read_whole(const char* path, uint8_t* dst, uint64_t n) {
+    const int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return errno ? errno : EIO;
+    uint64_t got = 0;
+    int err = 0;
+    while (got < n) {
+        const ssize_t k = read(fd, dst + got, n - got);
+        if (k < 0) {
+            if (errno == EINTR) continue;
+            err = errno ? errno : EIO;
+            break;
+        }
+        if (k == 0) {  // the file shrank after it was measured
+            err = EIO;
+            break;
+        }
+        got += (uint64_t)k;
+    }
+    close(fd);
+    return err;
+}
+
+// Read every file into dst + off[i] (size[i] bytes, as measured by bj_host_stat_files) and, when entries != NULL,
+// walk and hash it right away (bj_host_walk_batch_keys), while the kernel's copy is still in that core's cache.
+// status[i] = 0 or the errno of the failed open/read.
+extern "C" void bj_host_read_files(const char* const* paths, const uint64_t* size, const uint64_t* off, int n_files, uint8_t* dst,
+                                   int32_t* status, bj_host_entry* entries, int max_entries, int32_t* counts, uint64_t* key_hash,
+                                   int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_files) n_threads = n_files > 0 ? n_files : 1;
+    auto work = [&](int t) {
+        for (int i = t; i < n_files; i += n_threads) {
+            uint8_t* d = dst + off[i];
+            status[i] = read_whole(paths[i], d, size[i]);
+            if (!entries) continue;
+            bj_host_entry* e = entries + (size_t)i * max_entries;
+            counts[i] = status[i] ? 0 : walk_one(d, size[i], e, max_entries);
+            key_hash[2 * i] = key_hash[2 * i + 1] = 0;
+            if (counts[i] > 0) key_hash_one(d, e, counts[i], key_hash + 2 * i);
+        }
+    };
+    if (n_threads == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+}

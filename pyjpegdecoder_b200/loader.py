@@ -100,36 +100,44 @@ class _Uploader:
         while self.inflight_desc and self.inflight_desc[0][0].query():
             self.desc_free.append(self.inflight_desc.pop(0)[1])
 
-    def pack_stage(self, files: Sequence[Source], read_threads: int = 8):
-        """First half of the host side of a sub-batch (C code, releases the GIL): read, gather into a pinned buffer,
-        start the H2D copy of the file bytes."""
-        if any(not isinstance(f, (bytes, bytearray, memoryview)) for f in files) and len(files) > 1:
-            with ThreadPoolExecutor(min(read_threads, len(files))) as ex:
-                datas = list(ex.map(_read, files))
-        else:
-            datas = [_read(f) for f in files]
+    def pack_stage(self, files: Sequence[Source], read_threads: int = 16):
+        """First half of the host side of a sub-batch (C code / file I/O, releases the GIL): get the file bytes into a
+        pinned buffer and start their H2D copy.  Paths are read straight into the pinned buffer; bytes objects are
+        gathered into it."""
+        from .pipeline import read_files_packed
         self._reclaim(block=True)
-        packed = pack_files(datas, pin=True, reuse_slot="checkout", walk=len(datas) >= FAST_PLAN_MIN_FILES)
-        raw_host = packed[0]
+        datas = None
+        if len(files) >= FAST_PLAN_MIN_FILES and all(isinstance(f, (str, Path)) for f in files):
+            raw_host, offsets, sizes = read_files_packed(files)
+            packed = (raw_host, offsets)
+        else:
+            if any(not isinstance(f, (bytes, bytearray, memoryview)) for f in files) and len(files) > 1:
+                with ThreadPoolExecutor(min(read_threads, len(files))) as ex:
+                    datas = list(ex.map(_read, files))
+            else:
+                datas = [_read(f) for f in files]
+            packed = pack_files(datas, pin=True, reuse_slot="checkout", walk=len(datas) >= FAST_PLAN_MIN_FILES)
+            raw_host = packed[0]
+            sizes = [len(d) for d in datas]
         with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
             raw_dev = torch.empty(raw_host.numel(), dtype=torch.uint8, device=self.dev)
             raw_dev.copy_(raw_host, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self.inflight.append((ev, raw_host))
-        return list(files), datas, packed, raw_dev, ev
+        return list(files), datas, sizes, packed, raw_dev, ev
 
     def plan_stage(self, packed_stage):
-        """Second half (numpy / Python, holds the GIL): plan the sub-batch and upload its descriptors.  Runs on its own
-        thread so that it overlaps the gather of the next sub-batch.  packed_stage: pack_stage's result or its future."""
+        """Second half (numpy / Python, holds the GIL): plan the sub-batch and upload its descriptors.
+        packed_stage: pack_stage's result or its future."""
         from .pipeline import upload_descriptors
         if hasattr(packed_stage, "result"):
             packed_stage = packed_stage.result()
-        files, datas, packed, raw_dev, ev = packed_stage
+        files, datas, sizes, packed, raw_dev, ev = packed_stage
         raw_host, offsets = packed
-        if len(datas) >= FAST_PLAN_MIN_FILES:
+        if len(sizes) >= FAST_PLAN_MIN_FILES:
             from .fastplan import plan_batch
-            plan = plan_batch(raw_host, offsets, [len(d) for d in datas], walked=getattr(raw_host, "_bj_walk", None))
+            plan = plan_batch(raw_host, offsets, sizes, walked=getattr(raw_host, "_bj_walk", None))
         else:
             plan = BatchPlan([parse_jpeg(d) for d in datas], offsets, raw_host.numel())
         self._reclaim_desc()

@@ -159,3 +159,62 @@ def test_to_host_gives_the_same_arrays_through_one_copy_per_sub_batch():
         assert a._batch.host_image(a._index) is not None and b._batch.host_image(b._index) is not None
         assert a.image_array.shape == r.image_array.shape == b.image_array.shape
         assert np.array_equal(a.image_array, r.image_array) and np.array_equal(b.image_array, r.image_array)
+
+
+def test_read_files_packed_matches_the_files(tmp_path):
+    """Path inputs are read straight into the packed (pinned on a GPU box) buffer: offsets 16-byte aligned, bytes equal."""
+    import os
+    from pyjpegdecoder_b200.pipeline import read_files_packed
+    blobs = [os.urandom(n) for n in (1, 15, 16, 17, 4097, 70001, 0, 33)]
+    paths = []
+    for i, b in enumerate(blobs):
+        p = tmp_path / f"f{i}.bin"
+        p.write_bytes(b)
+        paths.append(p if i % 2 else str(p))
+    buf, offs, sizes = read_files_packed(paths, read_threads=4, walk=False)
+    raw = buf.numpy()
+    assert sizes == [len(b) for b in blobs] and all(o % 16 == 0 for o in offs)
+    for b, o in zip(blobs, offs):
+        assert bytes(raw[o:o + len(b)]) == b
+    with pytest.raises(OSError):
+        read_files_packed([tmp_path / "missing.bin"])
+
+
+@pytest.mark.gpu
+def test_stream_of_paths_reads_into_pinned_memory_and_matches_bytes(tmp_path):
+    from pyjpegdecoder_b200 import NotJpeg, decode_batch, decode_stream
+    datas = [_jpeg(48 + 8 * (i % 4), 40 + 8 * (i % 3), i, subsampling=2 if i % 2 else 0, progressive=(i % 5 == 0)) for i in range(19)]
+    paths = []
+    for i, d in enumerate(datas):
+        p = tmp_path / f"img{i}.jpg"
+        p.write_bytes(d)
+        paths.append(p)
+    ref = decode_batch(datas, device="cuda:0")
+    got = [d for part in decode_stream(paths, chunk=6, device="cuda:0") for d in part]
+    assert len(got) == len(ref)
+    for a, b, p in zip(got, ref, paths):
+        assert np.array_equal(a.image_array, b.image_array)
+        assert a.file_path == p
+    bad = tmp_path / "bad.jpg"
+    bad.write_bytes(b"definitely not a jpeg")
+    with pytest.raises(NotJpeg):
+        list(decode_stream(paths[:5] + [bad], chunk=6, device="cuda:0"))
+
+
+def test_read_files_packed_walks_like_the_batch_walker():
+    """The walk that rides along with the file reads (C threads, right after each read) equals the stand-alone walk of
+    the packed buffer: same entries, counts and key hashes -- so plan_batch builds the same plan either way."""
+    from conftest import GOLDEN
+    from pyjpegdecoder_b200.fastplan import plan_batch, walk_batch
+    from pyjpegdecoder_b200.pipeline import read_files_packed
+    paths = sorted((GOLDEN / "cases").glob("*.jpg"))[:12]
+    buf, offs, sizes = read_files_packed(paths, read_threads=3, walk=True)
+    entries, counts, hashes = buf._bj_walk
+    e2, c2, h2 = walk_batch(buf.numpy(), np.asarray(offs, dtype=np.uint64), np.asarray(sizes, dtype=np.uint64))
+    assert np.array_equal(counts, c2) and np.array_equal(hashes, h2)
+    for i in range(len(paths)):
+        assert np.array_equal(entries[i, :counts[i]], e2[i, :c2[i]])
+    a = plan_batch(buf, offs, sizes, walked=buf._bj_walk)
+    b = plan_batch(buf, offs, sizes)
+    assert len(a.parsed) == len(b.parsed) == len(paths)
+    assert [p.width for p in a.parsed] == [p.width for p in b.parsed]
