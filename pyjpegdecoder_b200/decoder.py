@@ -225,8 +225,21 @@ def decode_batch(files: Sequence[Union[str, Path, bytes]], device: Optional[Unio
         for part in decode_stream(files, chunk=chunk, device=device, keep_coefficients=keep_coefficients, to_host=to_host):
             out.extend(part)
         return out
-    datas = [_read(f) for f in files]
-    batch = decode_batch_on_device(datas, device=device)
+    from .pipeline import FAST_PLAN_MIN_FILES
+    if len(files) >= FAST_PLAN_MIN_FILES and all(isinstance(f, (str, Path)) for f in files):
+        # paths: the C helper's threads read the files straight into the pinned staging buffer and walk them
+        from .fastplan import plan_batch
+        from .pipeline import read_files_packed, release_pinned
+        raw, offs, sizes = read_files_packed(files)
+        try:
+            plan = plan_batch(raw, offs, sizes, walked=getattr(raw, "_bj_walk", None))
+        except Exception:
+            release_pinned(raw)
+            raise
+        batch = decode_batch_on_device(None, device=device, packed=(raw, offs), plan=plan)
+    else:
+        datas = [_read(f) for f in files]
+        batch = decode_batch_on_device(datas, device=device)
     if to_host:
         batch.start_host_copy()
     return [JpegDecoder(f, _batch=batch, _index=i) for i, f in enumerate(files)]

@@ -192,6 +192,8 @@ def test_stream_of_paths_reads_into_pinned_memory_and_matches_bytes(tmp_path):
     ref = decode_batch(datas, device="cuda:0")
     got = [d for part in decode_stream(paths, chunk=6, device="cuda:0") for d in part]
     assert len(got) == len(ref)
+    for a, b in zip(decode_batch(paths, device="cuda:0"), ref):       # the one-shot call reads paths the same way
+        assert np.array_equal(a.image_array, b.image_array)
     for a, b, p in zip(got, ref, paths):
         assert np.array_equal(a.image_array, b.image_array)
         assert a.file_path == p
