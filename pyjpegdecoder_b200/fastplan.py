@@ -191,7 +191,7 @@ class FastPlan:
         self.raw_bytes = int(raw.size)
         entries, counts, hashes = walked if walked is not None else walk_batch(raw, offsets, sizes, threads)
         if (counts == -1).any():
-            raise NotJpeg("File is not a JPEG image.")
+            raise NotJpeg(f"File {int(np.nonzero(counts == -1)[0][0])}: File is not a JPEG image.")
         if (counts < 0).any():
             raise _Fallback("marker walk overflow")
         # ---- templates: one per distinct key hash (no per-file Python work) -------------------------------
