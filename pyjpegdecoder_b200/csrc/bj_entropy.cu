@@ -102,6 +102,10 @@ struct StagedSrc {
     mutable uint32_t ready;  // the group being read has landed in the ring (a full register: a bool gets packed)
     // No waiting anywhere: a group that has not landed yet (the first one or two of a thread, before the producer has
     // seen it) is read from global memory instead.
+    // ONE seek per thread: the reader's look-ahead (BitReader::w2) may already have entered the next group, so a second
+    // seek at the reader's own position can land one group back, in a slot the producer has reused by then.
+    // write_kernel seeks once; a kernel that seeks twice (spec_kernel) would have to refuse groups below the highest
+    // one entered -- measured there, and slower than plain loads anyway (profiles/README.md).
     __device__ __forceinline__ void enter(uint32_t i) const {  // i = first word of the group
         sts_weak(flags, i);
         ready = lds_weak(flags + NT * 4) > i ? 1u : 0u;
