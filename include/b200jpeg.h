@@ -91,7 +91,7 @@ typedef struct bj_image {
  * (self-synchronising Huffman decode), see DESIGN.md.
  * ------------------------------------------------------------------------------------------- */
 #ifndef BJ_SUBSEQ_BITS
-#define BJ_SUBSEQ_BITS 4096   /* bj_sizeof_entropy(3) reports the value the library was built with */
+#define BJ_SUBSEQ_BITS 8192   /* bj_sizeof_entropy(3) reports the value the library was built with */
 #endif
 #ifndef BJ_ENTROPY_THREADS
 #define BJ_ENTROPY_THREADS 128 /* subsequences per CTA */
